@@ -1,0 +1,522 @@
+"""Tensor-level wrappers of the C ABI: allocation, shape checks, autograd glue.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic
+operation runs in libcnerf.so.  All tensors must be CUDA float32.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+_F32 = torch.float32
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != _F32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor; consistentnerf_b200 has no CPU path")
+
+
+# ----------------------------------------------------------------------------------------
+# ray preparation / sampling
+# ----------------------------------------------------------------------------------------
+def pack_rays(rays_o, rays_d, near: float, far: float, use_viewdirs: bool, ndc=None) -> torch.Tensor:
+    """[n,3],[n,3] -> [n,8|11] ray batch (render(), NP/run_nerf.py:101-126)."""
+    _need_cuda(rays_o, "pack_rays")
+    o, d = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3))
+    n = o.shape[0]
+    out = torch.empty((n, 11 if use_viewdirs else 8), device=o.device, dtype=_F32)
+    H, W, focal = (int(ndc[0]), int(ndc[1]), float(ndc[2])) if ndc is not None else (0, 0, 0.0)
+    call("cnerf_pack_rays", ptr(o), ptr(d), n, float(near), float(far), int(use_viewdirs), int(ndc is not None),
+         H, W, focal, ptr(out), stream())
+    return out
+
+
+def image_rays(H: int, W: int, K, c2w, near: float, far: float, use_viewdirs: bool, ndc: bool, device) -> torch.Tensor:
+    """Whole-image ray batch from a pose (get_rays + render(), NP/run_nerf_helpers.py:164-173)."""
+    Kf = _lib.host_floats([K[i][j] for i in range(3) for j in range(3)])
+    c2w = c2w.detach().cpu() if isinstance(c2w, torch.Tensor) else c2w
+    Pf = _lib.host_floats([c2w[i][j] for i in range(3) for j in range(4)])
+    out = torch.empty((H * W, 11 if use_viewdirs else 8), device=device, dtype=_F32)
+    call("cnerf_image_rays", int(H), int(W), Kf, Pf, float(near), float(far), int(use_viewdirs), int(ndc), ptr(out), stream())
+    return out
+
+
+def stratified(rays: torch.Tensor, t_vals: torch.Tensor, t_rand: Optional[torch.Tensor], lindisp: bool):
+    """K1: rays [n,8|11] -> z [n,S], pts [n,S,3]  (NP/run_nerf.py:360-384)."""
+    _need_cuda(rays, "stratified")
+    n, S = rays.shape[0], t_vals.shape[0]
+    z = torch.empty((n, S), device=rays.device, dtype=_F32)
+    pts = torch.empty((n, S, 3), device=rays.device, dtype=_F32)
+    tr = _f32c(t_rand) if t_rand is not None else None
+    call("cnerf_stratified_z", ptr(rays), rays.shape[1], ptr(_f32c(t_vals)), ptr(tr), n, S, int(bool(lindisp)),
+         ptr(z), ptr(pts), stream())
+    return z, pts
+
+
+def ray_points(rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    n, S = z.shape
+    pts = torch.empty((n, S, 3), device=rays.device, dtype=_F32)
+    call("cnerf_ray_points", ptr(rays), rays.shape[1], ptr(_f32c(z)), n, S, ptr(pts), stream())
+    return pts
+
+
+def sample_pdf(bins, weights, u: Optional[torch.Tensor], n_new: int, debug: bool = False):
+    """K5 stand-alone (NP/run_nerf_helpers.py:206-250).  u None => deterministic linspace."""
+    _need_cuda(bins, "sample_pdf")
+    bins, weights = _f32c(bins), _f32c(weights)
+    n, B = bins.shape
+    if weights.shape != (n, B - 1):
+        raise ValueError(f"sample_pdf: weights {tuple(weights.shape)} must be [n, bins-1] = {(n, B - 1)}")
+    dev = bins.device
+    u_det = None
+    if u is None:
+        u_det = torch.linspace(0.0, 1.0, n_new, device=dev, dtype=_F32)
+    else:
+        u = _f32c(u)
+    out = torch.empty((n, n_new), device=dev, dtype=_F32)
+    cdf = torch.empty((n, B), device=dev, dtype=_F32) if debug else None
+    below = torch.empty((n, n_new), device=dev, dtype=torch.int32) if debug else None
+    above = torch.empty((n, n_new), device=dev, dtype=torch.int32) if debug else None
+    call("cnerf_sample_pdf", ptr(bins), ptr(weights), ptr(u), ptr(u_det), n, B, n_new, ptr(out), ptr(cdf),
+         ptr(below), ptr(above), stream())
+    if debug:
+        return out, {"cdf": cdf, "below": below, "above": above}
+    return out
+
+
+def sample_fine(z: torch.Tensor, weights: torch.Tensor, u: Optional[torch.Tensor], n_new: int):
+    """Fused mid-bins + inverse CDF + sorted merge + std (NP/run_nerf.py:393-399,415)."""
+    n, S = z.shape
+    dev = z.device
+    u_det = torch.linspace(0.0, 1.0, n_new, device=dev, dtype=_F32) if u is None else None
+    uu = _f32c(u) if u is not None else None
+    z_samples = torch.empty((n, n_new), device=dev, dtype=_F32)
+    z_fine = torch.empty((n, S + n_new), device=dev, dtype=_F32)
+    z_std = torch.empty((n,), device=dev, dtype=_F32)
+    call("cnerf_sample_fine", ptr(_f32c(z)), ptr(_f32c(weights)), ptr(uu), ptr(u_det), n, S, n_new, ptr(z_samples),
+         ptr(z_fine), ptr(z_std), stream())
+    return z_samples, z_fine, z_std
+
+
+# ----------------------------------------------------------------------------------------
+# positional encoding + generic layers
+# ----------------------------------------------------------------------------------------
+def posenc(x: torch.Tensor, n_freqs: int, repeat: int = 1, out: Optional[torch.Tensor] = None, col0: int = 0):
+    """K2: [n,C] -> [n*repeat, C*(1+2L)] (optionally into columns col0.. of a wider buffer)."""
+    _need_cuda(x, "posenc")
+    x = _f32c(x)
+    n, C = x.shape
+    E = C * (1 + 2 * n_freqs)
+    rows = n * repeat
+    if out is None:
+        out = torch.empty((rows, E), device=x.device, dtype=_F32)
+    call("cnerf_posenc", ptr(x), x.stride(0), rows, C, n_freqs, repeat, ptr(out), out.stride(0), col0, stream())
+    return out
+
+
+def linear_fwd(x, w, b, relu: bool, out: Optional[torch.Tensor] = None):
+    """y = act(x w^T + b); x may be a column slice of a wider row-major buffer (stride(1)==1)."""
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=_F32)
+    call("cnerf_linear_fwd", ctypes.c_void_p(x.data_ptr()), x.stride(0), ptr(w), ptr(b), m, n, k, int(relu),
+         ctypes.c_void_p(out.data_ptr()), out.stride(0), stream())
+    return out
+
+
+def linear_bwd_data(dy, y_mask, w, dx: torch.Tensor, accumulate: bool):
+    m, n = dy.shape
+    k = w.shape[1]
+    call("cnerf_linear_bwd_data", ctypes.c_void_p(dy.data_ptr()), dy.stride(0),
+         ctypes.c_void_p(y_mask.data_ptr()) if y_mask is not None else None,
+         y_mask.stride(0) if y_mask is not None else 0, ptr(w), m, n, k,
+         ctypes.c_void_p(dx.data_ptr()), dx.stride(0), int(accumulate), stream())
+    return dx
+
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def linear_bwd_weight(dy, y_mask, x, dw: torch.Tensor, db: Optional[torch.Tensor], accumulate: bool):
+    m, n = dy.shape
+    k = x.shape[1]
+    need = int(_lib.load().cnerf_linear_bwd_weight_workspace(m, n, k))
+    ws = _workspace(dy.device, need)
+    call("cnerf_linear_bwd_weight", ctypes.c_void_p(dy.data_ptr()), dy.stride(0),
+         ctypes.c_void_p(y_mask.data_ptr()) if y_mask is not None else None,
+         y_mask.stride(0) if y_mask is not None else 0,
+         ctypes.c_void_p(x.data_ptr()), x.stride(0), m, n, k, ptr(dw), ptr(db), int(accumulate), ptr(ws), stream())
+
+
+# ----------------------------------------------------------------------------------------
+# layer-wise MLP engine (any architecture): forward keeps the activations, backward walks them
+# ----------------------------------------------------------------------------------------
+class MLPSpec:
+    """Static description of one NeRF network (NP/run_nerf_helpers.py:67-101)."""
+
+    def __init__(self, D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs):
+        self.D, self.W, self.input_ch, self.input_ch_views = D, W, input_ch, input_ch_views
+        self.output_ch, self.skips, self.use_viewdirs = output_ch, tuple(skips), use_viewdirs
+
+    def param_names(self) -> List[str]:
+        names = []
+        for i in range(self.D):
+            names += [f"pts_linears.{i}.weight", f"pts_linears.{i}.bias"]
+        if self.use_viewdirs:
+            names += ["feature_linear.weight", "feature_linear.bias", "alpha_linear.weight", "alpha_linear.bias",
+                      "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
+        else:
+            names += ["output_linear.weight", "output_linear.bias"]
+        return names
+
+    @property
+    def is_canonical(self) -> bool:
+        """The architecture the fused tcgen05 kernel is specialised for."""
+        return (self.D == 8 and self.W == 256 and self.input_ch == 63 and self.input_ch_views == 27
+                and self.skips == (4,) and self.use_viewdirs)
+
+
+def _layerwise_forward(spec: MLPSpec, P: dict, x: torch.Tensor):
+    """x [m, input_ch+input_ch_views] -> (out, saved activations).  Concatenations are laid out
+    in place: a skip layer writes its output next to a copy of the encoded input."""
+    m = x.shape[0]
+    dev = x.device
+    W, ic, icv = spec.W, spec.input_ch, spec.input_ch_views
+    x_pts = x[:, :ic]
+    acts = []                      # per pts layer: (input view, output view)
+    h_in = x_pts
+    for i in range(spec.D):
+        if i in spec.skips:
+            buf = torch.empty((m, ic + W), device=dev, dtype=_F32)
+            buf[:, :ic].copy_(x_pts)
+            out = buf[:, ic:]
+            nxt = buf
+        else:
+            out = torch.empty((m, W), device=dev, dtype=_F32)
+            nxt = out
+        linear_fwd(h_in, P[f"pts_linears.{i}.weight"], P[f"pts_linears.{i}.bias"], True, out)
+        acts.append((h_in, out))
+        h_in = nxt
+    saved = {"acts": acts, "h_last": h_in}
+    if spec.use_viewdirs:
+        result = torch.empty((m, 4), device=dev, dtype=_F32)
+        sigma = linear_fwd(h_in, P["alpha_linear.weight"], P["alpha_linear.bias"], False)
+        vbuf = torch.empty((m, W + icv), device=dev, dtype=_F32)
+        linear_fwd(h_in, P["feature_linear.weight"], P["feature_linear.bias"], False, vbuf[:, :W])
+        vbuf[:, W:].copy_(x[:, ic:ic + icv])
+        hv = linear_fwd(vbuf, P["views_linears.0.weight"], P["views_linears.0.bias"], True)
+        rgb = linear_fwd(hv, P["rgb_linear.weight"], P["rgb_linear.bias"], False)
+        result[:, :3].copy_(rgb)
+        result[:, 3:].copy_(sigma)
+        saved.update({"vbuf": vbuf, "hv": hv})
+    else:
+        result = linear_fwd(h_in, P["output_linear.weight"], P["output_linear.bias"], False)
+    return result, saved
+
+
+def _layerwise_backward(spec: MLPSpec, P: dict, saved: dict, d_out: torch.Tensor, grads: dict, need_dx: bool,
+                        accumulate: bool):
+    """Accumulates parameter gradients into ``grads`` (name -> tensor); returns d_x or None."""
+    dev = d_out.device
+    m = d_out.shape[0]
+    W, ic, icv = spec.W, spec.input_ch, spec.input_ch_views
+    h_last = saved["h_last"]
+    d_h = torch.empty((m, W), device=dev, dtype=_F32)
+    d_views = None
+    if spec.use_viewdirs:
+        d_rgb = d_out[:, :3].contiguous()
+        d_sigma = d_out[:, 3:4].contiguous()
+        hv, vbuf = saved["hv"], saved["vbuf"]
+        linear_bwd_weight(d_rgb, None, hv, grads["rgb_linear.weight"], grads["rgb_linear.bias"], accumulate)
+        d_hv = torch.empty_like(hv)
+        linear_bwd_data(d_rgb, None, P["rgb_linear.weight"], d_hv, False)
+        linear_bwd_weight(d_hv, hv, vbuf, grads["views_linears.0.weight"], grads["views_linears.0.bias"], accumulate)
+        d_vbuf = torch.empty_like(vbuf)
+        linear_bwd_data(d_hv, hv, P["views_linears.0.weight"], d_vbuf, False)
+        d_feat = d_vbuf[:, :W]
+        d_views = d_vbuf[:, W:]
+        h_feat_in = h_last if h_last.shape[1] == W else h_last[:, ic:]   # skip at the last layer is not used in practice
+        linear_bwd_weight(d_feat, None, h_feat_in, grads["feature_linear.weight"], grads["feature_linear.bias"], accumulate)
+        linear_bwd_data(d_feat, None, P["feature_linear.weight"], d_h, False)
+        linear_bwd_weight(d_sigma, None, h_feat_in, grads["alpha_linear.weight"], grads["alpha_linear.bias"], accumulate)
+        linear_bwd_data(d_sigma, None, P["alpha_linear.weight"], d_h, True)
+    else:
+        linear_bwd_weight(d_out, None, h_last, grads["output_linear.weight"], grads["output_linear.bias"], accumulate)
+        d_full = torch.empty((m, h_last.shape[1]), device=dev, dtype=_F32)
+        linear_bwd_data(d_out, None, P["output_linear.weight"], d_full, False)
+        d_h = d_full if d_full.shape[1] == W else d_full[:, ic:]
+    d_pts = torch.zeros((m, ic), device=dev, dtype=_F32) if need_dx else None
+    for i in reversed(range(spec.D)):
+        h_in, out = saved["acts"][i]
+        wn, bn = f"pts_linears.{i}.weight", f"pts_linears.{i}.bias"
+        linear_bwd_weight(d_h, out, h_in, grads[wn], grads[bn], accumulate)
+        if i == 0:
+            if need_dx:
+                linear_bwd_data(d_h, out, P[wn], d_pts, True)
+            break
+        d_in = torch.empty((m, h_in.shape[1]), device=dev, dtype=_F32)
+        linear_bwd_data(d_h, out, P[wn], d_in, False)
+        if (i - 1) in spec.skips:            # this layer's input was cat([pts, h]): split the gradient
+            if need_dx:
+                d_pts += d_in[:, :ic]
+            d_h = d_in[:, ic:]
+        else:
+            d_h = d_in
+    if not need_dx:
+        return None
+    d_x = torch.zeros((m, ic + icv), device=dev, dtype=_F32)
+    d_x[:, :ic] = d_pts
+    if d_views is not None and icv > 0:
+        d_x[:, ic:] = d_views
+    return d_x
+
+
+class LayerwiseMLPFn(torch.autograd.Function):
+    """NeRF.forward on pre-encoded inputs through the generic fp32 layer kernels."""
+
+    @staticmethod
+    def forward(ctx, spec: MLPSpec, x: torch.Tensor, *params: torch.Tensor):
+        names = spec.param_names()
+        P = {n: _f32c(p.detach()) for n, p in zip(names, params)}
+        xc = _f32c(x.detach())
+        out, saved = _layerwise_forward(spec, P, xc)
+        ctx.spec, ctx.P, ctx.saved_acts, ctx.xc = spec, P, saved, xc
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        spec, P = ctx.spec, ctx.P
+        d_out = _f32c(d_out)
+        grads = {n: torch.empty_like(p) for n, p in P.items()}
+        d_x = _layerwise_backward(spec, P, ctx.saved_acts, d_out, grads, ctx.x_needs_grad, False)
+        return (None, d_x) + tuple(grads[n] for n in spec.param_names())
+
+
+# ----------------------------------------------------------------------------------------
+# fused tcgen05 MLP (canonical architecture)
+# ----------------------------------------------------------------------------------------
+class PackedWeights:
+    """Owner of one cnerf_weights handle; repacks when the parameters changed in place."""
+
+    def __init__(self):
+        h = ctypes.c_void_p()
+        call("cnerf_weights_create", ctypes.byref(h))
+        self.handle = h
+        self._key = None
+        self._finalizer = weakref.finalize(self, _lib.load().cnerf_weights_destroy, h)
+
+    def refresh(self, P: dict, force: bool = False):
+        tensors = [P[f"pts_linears.{i}.weight"] for i in range(8)] + [P[f"pts_linears.{i}.bias"] for i in range(8)] + [
+            P["feature_linear.weight"], P["feature_linear.bias"], P["alpha_linear.weight"], P["alpha_linear.bias"],
+            P["views_linears.0.weight"], P["views_linears.0.bias"], P["rgb_linear.weight"], P["rgb_linear.bias"]]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if not force and key == self._key:
+            return
+        for t in tensors:
+            if not (t.is_cuda and t.dtype == _F32 and t.is_contiguous()):
+                raise RuntimeError("fused MLP needs contiguous CUDA fp32 parameters")
+        pw = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in tensors[:8]])
+        pb = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in tensors[8:16]])
+        call("cnerf_weights_refresh", self.handle, pw, pb, *[ptr(t) for t in tensors[16:]], stream())
+        self._key = key
+
+
+def fused_mlp_forward(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor) -> torch.Tensor:
+    """pts [n,S,3], viewdirs [n,3] -> raw [n,S,4] (K2+K3 on tensor cores)."""
+    n, S = pts.shape[0], pts.shape[1]
+    raw = torch.empty((n, S, 4), device=pts.device, dtype=_F32)
+    call("cnerf_mlp_fwd", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), stream())
+    return raw
+
+
+BWD_CHUNK_POINTS = 1 << 18      # activation recompute granularity of the backward pass
+
+
+class FusedMLPFn(torch.autograd.Function):
+    """run_network (embed + NeRF) with the tcgen05 forward.  Backward recomputes the activations
+    chunk by chunk with the fp32 layer kernels and accumulates the parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, spec: MLPSpec, packed: PackedWeights, multires: int, multires_views: int, pts, viewdirs, *params):
+        names = spec.param_names()
+        P = {n: p.detach() for n, p in zip(names, params)}
+        packed.refresh(P)
+        pts_c, vd_c = _f32c(pts.detach()), _f32c(viewdirs.detach())
+        raw = fused_mlp_forward(packed, pts_c, vd_c)
+        ctx.spec, ctx.P, ctx.enc = spec, P, (multires, multires_views)
+        ctx.save_for_backward(pts_c, vd_c)
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        spec, P = ctx.spec, ctx.P
+        L, Lv = ctx.enc
+        pts, viewdirs = ctx.saved_tensors
+        n, S = pts.shape[0], pts.shape[1]
+        d_raw = _f32c(d_raw).reshape(n * S, 4)
+        grads = {k: torch.zeros_like(v) for k, v in P.items()}
+        rays_per_chunk = max(1, BWD_CHUNK_POINTS // S)
+        first = True
+        for r0 in range(0, n, rays_per_chunk):
+            r1 = min(n, r0 + rays_per_chunk)
+            m = (r1 - r0) * S
+            x = torch.empty((m, spec.input_ch + spec.input_ch_views), device=pts.device, dtype=_F32)
+            posenc(pts[r0:r1].reshape(m, 3), L, 1, x, 0)
+            posenc(viewdirs[r0:r1], Lv, S, x, spec.input_ch)
+            _, saved = _layerwise_forward(spec, P, x)
+            _layerwise_backward(spec, P, saved, d_raw[r0 * S:r1 * S], grads, False, not first)
+            first = False
+        return (None, None, None, None, None, None) + tuple(grads[k] for k in spec.param_names())
+
+
+# ----------------------------------------------------------------------------------------
+# K4 compositing
+# ----------------------------------------------------------------------------------------
+class CompositeFn(torch.autograd.Function):
+    """raw2outputs (NP/run_nerf.py:265-308): returns rgb, disp, acc, weights, depth."""
+
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, noise, white_bkgd: bool):
+        _need_cuda(raw, "raw2outputs")
+        raw_c, z_c = _f32c(raw.detach()), _f32c(z.detach())
+        n, S = z_c.shape
+        d = rays_d.detach()
+        if d.dtype != _F32 or d.stride(-1) != 1:
+            d = _f32c(d)
+        noise_c = _f32c(noise.detach()) if noise is not None else None
+        dev = raw.device
+        rgb = torch.empty((n, 3), device=dev, dtype=_F32)
+        disp, acc, depth = (torch.empty((n,), device=dev, dtype=_F32) for _ in range(3))
+        weights = torch.empty((n, S), device=dev, dtype=_F32)
+        call("cnerf_composite_fwd", ptr(raw_c), ptr(z_c), ctypes.c_void_p(d.data_ptr()), d.stride(0), ptr(noise_c), n, S,
+             int(bool(white_bkgd)), ptr(rgb), ptr(disp), ptr(acc), ptr(depth), ptr(weights), stream())
+        ctx.save_for_backward(raw_c, z_c, d, noise_c)
+        ctx.white = bool(white_bkgd)
+        return rgb, disp, acc, weights, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth):
+        raw, z, d, noise = ctx.saved_tensors
+        n, S = z.shape
+
+        def opt(g):
+            return _f32c(g) if g is not None else None
+
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else torch.zeros((n, 3), device=raw.device, dtype=_F32)
+        d_raw = torch.empty_like(raw)
+        call("cnerf_composite_bwd", ptr(raw), ptr(z), ctypes.c_void_p(d.data_ptr()), d.stride(0), ptr(noise), n, S,
+             int(ctx.white), ptr(g_rgb), ptr(opt(g_disp)), ptr(opt(g_acc)), ptr(opt(g_depth)), ptr(opt(g_weights)),
+             ptr(d_raw), stream())
+        return d_raw, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# K6 / K7
+# ----------------------------------------------------------------------------------------
+def project_gather(pts_w, w2c, K, H: int, W: int, img=None, depth=None, c2w=None):
+    """World points [R,3] -> dict(px, py, mask(uint8), cam[R,3], rgb[R,C], depth[R], rays_o, rays_d)."""
+    _need_cuda(pts_w, "project_gather")
+    pts_w = _f32c(pts_w.reshape(-1, 3))
+    n = pts_w.shape[0]
+    dev = pts_w.device
+    w2c_h = _lib.host_floats(torch.as_tensor(w2c).detach().cpu().reshape(-1)[:16].tolist())
+    K_h = _lib.host_floats(torch.as_tensor(K).detach().cpu().reshape(-1)[:9].tolist())
+    c2w_h = _lib.host_floats(torch.as_tensor(c2w).detach().cpu().reshape(-1)[:12].tolist()) if c2w is not None else None
+    out = {"px": torch.empty(n, device=dev, dtype=_F32), "py": torch.empty(n, device=dev, dtype=_F32),
+           "mask": torch.empty(n, device=dev, dtype=torch.uint8), "cam": torch.empty((n, 3), device=dev, dtype=_F32)}
+    C = 0
+    if img is not None:
+        img = _f32c(img)
+        C = img.shape[0]
+        out["rgb"] = torch.empty((n, C), device=dev, dtype=_F32)
+    if depth is not None:
+        depth = _f32c(depth)
+        out["depth"] = torch.empty(n, device=dev, dtype=_F32)
+    if c2w is not None:
+        out["rays_o"] = torch.empty((n, 3), device=dev, dtype=_F32)
+        out["rays_d"] = torch.empty((n, 3), device=dev, dtype=_F32)
+    call("cnerf_project_gather", ptr(pts_w), n, w2c_h, K_h, c2w_h, ptr(img), C, ptr(depth), int(H), int(W),
+         ptr(out["px"]), ptr(out["py"]), ptr(out["mask"]), ptr(out["cam"]), ptr(out.get("rgb")), ptr(out.get("depth")),
+         ptr(out.get("rays_o")), ptr(out.get("rays_d")), stream())
+    return out
+
+
+def hard_mask_pair(rays_o, rays_d, depth_tgt, w2c_ref, K, depth_ref, thr0: float = 0.1, chunk: int = 5120,
+                   mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One (target, reference) pair of the hard-mask precompute (NP/run_nerf_view.py:1014-1041).
+    Passing ``mask`` ORs into it (the loop's ``mask_tgt += mask_tgt_mid``)."""
+    _need_cuda(rays_o, "hard_mask_pair")
+    o, d, dt = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3)), _f32c(depth_tgt.reshape(-1))
+    depth_ref = _f32c(depth_ref)
+    H, W = depth_ref.shape
+    n = dt.shape[0]
+    acc = mask is not None
+    if mask is None:
+        mask = torch.empty(n, device=o.device, dtype=torch.uint8)
+    w2c_h = _lib.host_floats(torch.as_tensor(w2c_ref).detach().cpu().reshape(-1)[:16].tolist())
+    K_h = _lib.host_floats(torch.as_tensor(K).detach().cpu().reshape(-1)[:9].tolist())
+    call("cnerf_hard_mask_pair", ptr(o), ptr(d), ptr(dt), n, w2c_h, K_h, ptr(depth_ref), int(H), int(W), float(thr0),
+         int(chunk), int(acc), ptr(mask), stream())
+    return mask
+
+
+class MaskedMSEFn(torch.autograd.Function):
+    """K7: masked / hard-mask-weighted MSE (NP/run_nerf_view.py:1645-1648,1737)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask, divisor: float, coef: float, n_ref: float, use_unmasked: bool):
+        _need_cuda(pred, "masked_mse")
+        p = _f32c(pred.detach())
+        p2 = p.reshape(p.shape[0], -1)
+        t2 = _f32c(target.detach()).reshape(p2.shape)
+        m = _f32c(mask.detach().reshape(-1)) if mask is not None else None
+        n, C = p2.shape
+        out = torch.empty(5, device=p.device, dtype=_F32)
+        ws = _workspace(p.device, 8192)
+        call("cnerf_masked_mse_fwd", ptr(p2), ptr(t2), ptr(m), n, C, float(divisor), float(coef), float(n_ref),
+             int(use_unmasked), ptr(out), ptr(ws), stream())
+        ctx.save_for_backward(p2, t2, m, out)
+        ctx.cfg = (float(divisor), float(coef), float(n_ref), int(use_unmasked), pred.shape)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        p2, t2, m, out = ctx.saved_tensors
+        divisor, coef, n_ref, use_unmasked, shape = ctx.cfg
+        n, C = p2.shape
+        g = _f32c(g_loss).reshape(1)
+        d = torch.empty_like(p2)
+        call("cnerf_masked_mse_bwd", ptr(p2), ptr(t2), ptr(m), n, C, divisor, coef, n_ref, use_unmasked, ptr(out), ptr(g),
+             ptr(d), stream())
+        return d.reshape(shape), None, None, None, None, None, None
+
+
+def umma_selftest(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """d = a b^T through the tcgen05 building blocks (a [128,k], b [n,k])."""
+    a, b = _f32c(a), _f32c(b)
+    d = torch.empty((128, b.shape[0]), device=a.device, dtype=_F32)
+    call("cnerf_umma_selftest", ptr(a), ptr(b), b.shape[0], a.shape[1], ptr(d), stream())
+    return d

@@ -120,10 +120,11 @@ def mlp_forward(params: Dict[str, torch.Tensor], x: torch.Tensor, D=8, W=256, in
 # stratified sampling  (NP/run_nerf.py:360-384)
 # --------------------------------------------------------------------------------------
 def stratified_z(near: torch.Tensor, far: torch.Tensor, n_samples: int, lindisp: bool = False,
-                 t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 t_rand: Optional[torch.Tensor] = None, t_vals: Optional[torch.Tensor] = None) -> torch.Tensor:
     """near/far [N,1] -> z [N,S].  ``t_rand`` [N,S] in [0,1) switches the jitter on
-    (perturb > 0 branch, :368-382); None keeps the bin edges (:361-366)."""
-    t = torch.linspace(0.0, 1.0, n_samples, dtype=near.dtype)
+    (perturb > 0 branch, :368-382); None keeps the bin edges (:361-366).  ``t_vals`` overrides
+    the linspace (CPU and CUDA linspace may differ in the last bit)."""
+    t = torch.linspace(0.0, 1.0, n_samples, dtype=near.dtype) if t_vals is None else t_vals.to(near.dtype)
     if lindisp:
         z = 1.0 / (1.0 / near * (1.0 - t) + 1.0 / far * t)
     else:
@@ -376,14 +377,14 @@ def hard_mask_pair(rays_o, rays_d, depth_tgt, w2c_ref, K, ref_depth_hw, thr0: fl
 # masked consistency losses  (NP/run_nerf_view.py:1645-1648,1737; cal_correspondance :1516-1517,1550-1551)
 # --------------------------------------------------------------------------------------
 def masked_mse(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, coef: float,
-               n_ref: int, scale: float = 1.0, use_unmasked: bool = True) -> torch.Tensor:
-    """mean((pred-target)^2 * scale^2) over mask==1 rows, plus ``coef`` times the same
-    over mask==0 rows when mask.sum() != n_ref.  ``scale`` = 1/far for the depth term."""
+               n_ref: int, divisor: float = 1.0, use_unmasked: bool = True) -> torch.Tensor:
+    """mean((pred/divisor-target/divisor)^2) over mask==1 rows, plus ``coef`` times the same
+    over mask==0 rows when mask.sum() != n_ref.  ``divisor`` = far for the depth term."""
     m1 = mask.reshape(-1) == 1
     m0 = mask.reshape(-1) == 0
-    loss = torch.mean((pred[m1] * scale - target[m1] * scale) ** 2)
+    loss = torch.mean((pred[m1] / divisor - target[m1] / divisor) ** 2)
     if use_unmasked and float(mask.sum()) != n_ref:
-        loss = loss + coef * torch.mean((pred[m0] * scale - target[m0] * scale) ** 2)
+        loss = loss + coef * torch.mean((pred[m0] / divisor - target[m0] / divisor) ** 2)
     return loss
 
 

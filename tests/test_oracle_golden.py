@@ -117,6 +117,6 @@ def test_masked_losses():
     close(li, g["img_loss"], rtol=1e-6)
     close(O.mse_to_psnr(li), g["psnr"].reshape(()), rtol=1e-6)
     d, q = t(g["depth"]), t(g["depth_prior"])
-    close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], scale=1 / far, use_unmasked=False),
-          g["depth_loss_masked_only"], rtol=1e-5)
-    close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], scale=1 / far), g["depth_loss_both"], rtol=1e-5)
+    close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], divisor=far, use_unmasked=False),
+          g["depth_loss_masked_only"], rtol=1e-6)
+    close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], divisor=far), g["depth_loss_both"], rtol=1e-6)
