@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray hot path (BASELINE.json: rays/s on 4096-ray x (64 coarse + 128 fine) batches).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode train|render] [--impl b200|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A *step* is one pass of the
+whole hot path over one batch of 4096 synthetic rays per GPU (workload A of SURVEY.md section 8d):
+
+  train  (default)  render() -> masked RGB + depth consistency losses (coarse and fine) -> backward ->
+                    one all-reduce of the flat MLP gradient (N > 1) -> Adam step
+  render            render() under no_grad with perturb=0 (novel-view path)
+
+``value`` is timed with the batch already resident in HBM; ``e2e`` copies the batch from pinned host
+memory every step and reads the loss (train) / rgb (render) back, through the same public API.
+``--impl reference`` times the CPU oracle port of the reference (oracle/nerf_oracle.py) on a bounded
+sample of the same workload on the host cores (the reference itself cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_RAYS, N_SAMPLES, N_IMPORTANCE = 4096, 64, 128
+FLOP_PER_POINT = 1_186_816
+FLOP_PER_RAY_FWD = FLOP_PER_POINT * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
+NEAR, FAR, COEF = 2.0, 6.0, 0.2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("bf16_tflops_sustained", p["bf16_tflops"]), p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_batch(n, seed):
+    from util import workload_rays
+    o, d = workload_rays(n, seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    tgt = torch.rand(n, 3, generator=g)
+    depth_prior = 2.5 + 3.0 * torch.rand(n, generator=g)
+    mask = (torch.rand(n, 1, generator=g) > 0.3).float()      # hard mask: ~70 % consistent pixels
+    return o, d, tgt, depth_prior, mask
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU baseline)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import consistentnerf_b200 as cn
+    from consistentnerf_b200 import _lib
+    from consistentnerf_b200.distributed import FlatGrads
+    from oracle import nerf_oracle as O                        # parameters + cpu_baseline leg only
+    from util import ARCH, module_from_params
+
+    train = args.mode == "train"
+    pc, pf = O.make_params(0, sigma_bias=0.5, **ARCH), O.make_params(1, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH, dev), module_from_params(pf, ARCH, dev)
+    embed_fn, _ = cn.get_embedder(10, 0)
+    embeddirs_fn, _ = cn.get_embedder(4, 0)
+
+    def query(inputs, viewdirs, network_fn):
+        return cn.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn)
+    kw = dict(network_query_fn=query, perturb=1.0 if train else 0.0, N_importance=N_IMPORTANCE, network_fine=fine,
+              N_samples=N_SAMPLES, network_fn=coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0.0,
+              ndc=False, lindisp=False, near=NEAR, far=FAR)
+    hot = [p for net in (coarse, fine) for n_, p in net.named_parameters() if n_ in net.spec.param_names()]
+    flat = FlatGrads(hot) if train else None
+    opt = torch.optim.Adam(hot, lr=5e-4, betas=(0.9, 0.999)) if train else None
+
+    n_batches = 8                                              # distinct batches, rotated
+    host = [tuple(x.pin_memory() for x in make_batch(N_RAYS, 100 * rank + b)) for b in range(n_batches)]
+    resident = [tuple(x.to(dev) for x in hb) for hb in host]
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(batch):
+        o, d, tgt, prior, mask = batch
+        if train:
+            flat.zero_()
+            rgb, disp, acc, depth, ex = cn.render(1, N_RAYS, None, chunk=32768, rays=(o, d), retraw=True, **kw)
+            loss = (cn.masked_img_loss(rgb, tgt, mask, COEF) + cn.masked_img_loss(ex["rgb0"], tgt, mask, COEF)
+                    + cn.masked_depth_loss(depth, prior, mask, FAR, COEF, include_unmasked=True)
+                    + cn.masked_depth_loss(ex["depth0"], prior, mask, FAR, COEF, include_unmasked=True))
+            loss.backward()
+            if world > 1:
+                flat.allreduce(average=True)
+            opt.step()
+            return loss
+        with torch.no_grad():
+            rgb, disp, acc, depth, ex = cn.render(1, N_RAYS, None, chunk=32768, rays=(o, d), **kw)
+        return rgb
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e: bool):
+        for w in range(args.warmup):
+            r = step(tuple(x.to(dev, non_blocking=True) for x in host[w % n_batches]) if e2e else resident[w % n_batches])
+            if e2e:
+                r.cpu()
+        sync_all()
+        _lib.launch_count = 0
+        _lib.event_trace.clear()
+        if not e2e:
+            _lib.event_trace["cnerf_mlp_fwd"] = []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k in range(args.steps):
+            if e2e:
+                r = step(tuple(x.to(dev, non_blocking=True) for x in host[k % n_batches]))
+                r.cpu()                                         # loss (train) or rgb (render) back on the host
+            else:
+                l2_flush.zero_()                                # flush L2 between timed iterations
+                step(resident[k % n_batches])
+        t1.record()
+        sync_all()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / args.steps
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ms_step = timed(False)
+    launches = _lib.launch_count
+    mlp_events = _lib.event_trace.pop("cnerf_mlp_fwd", [])
+    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events) / max(1, len(mlp_events))     # mean over coarse+fine launches
+    mlp_ms_step = sum(a.elapsed_time(b) for a, b in mlp_events) / args.steps
+    ms_e2e = timed(True)
+    clk = clocks.stop() if rank == 0 else None
+    # the l2 flush memset is inside the device-timed loop; measure and subtract nothing: report as is
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tf_peak, hbm_peak, peak_src = peaks()
+    flops_per_launch = FLOP_PER_RAY_FWD * N_RAYS / 2.0          # two launches/step (coarse 64 + fine 192 pts): mean
+    achieved = flops_per_launch / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    rays_per_s = N_RAYS * world / (ms_step * 1e-3)
+    e2e_rays = N_RAYS * world / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+    d2h = 4 if train else N_RAYS * 3 * 4
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = run_reference(args, sample_rays=256, steps=2, warmup=1, quiet=True)
+    line = {
+        "metric": "rays/sec", "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32 (fp16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"A: {N_RAYS} rays/GPU x ({N_SAMPLES} coarse + {N_IMPORTANCE} fine), viewdirs, 8x256 coarse+fine MLPs, "
+                               + ("train step: render + masked rgb/depth losses + backward + grad all-reduce + Adam" if train
+                                  else "render-only, no_grad, perturb=0"),
+                   "mode": args.mode, "rays_per_gpu": N_RAYS, "parallelism": f"ray-tile dp{world}",
+                   "l2": "256 MiB memset between timed iterations (value); e2e streams fresh host batches"},
+        "e2e": {"value": e2e_rays, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"kernel": "mlp_fused_kernel (K2+K3 forward, tcgen05)", "bound": "tensor", "achieved": achieved,
+                     "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                     "peak_source": peak_src, "kernel_ms_per_step": mlp_ms_step,
+                     "note": "algorithmic fp32 FLOPs (1 186 816/point); the kernel issues 3 fp16 MMAs per MAC"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: CPU oracle port of the reference path
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, sample_rays=256, steps=None, warmup=None, quiet=False):
+    from oracle import nerf_oracle as O
+    from util import ARCH
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    train = args.mode == "train"
+    pc, pf = O.make_params(0, sigma_bias=0.5, **ARCH), O.make_params(1, sigma_bias=0.5, **ARCH)
+    names = [k for k in pc if k not in ("temp_rgb", "temp_depth", "depth_scale")]
+    if train:
+        for p in (pc, pf):
+            for k in names:
+                p[k].requires_grad_(True)
+        opt = torch.optim.Adam([p[k] for p in (pc, pf) for k in names], lr=5e-4, betas=(0.9, 0.999))
+    gen = torch.Generator().manual_seed(0)
+
+    def step(i):
+        o, d, tgt, prior, mask = make_batch(sample_rays, i)
+        rays = O.pack_rays(o, d, NEAR, FAR, True)
+        if train:
+            opt.zero_grad()
+            out = O.render_rays(rays, pc, pf, ARCH, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, white_bkgd=True,
+                                t_rand=torch.rand(sample_rays, N_SAMPLES, generator=gen),
+                                u=torch.rand(sample_rays, N_IMPORTANCE, generator=gen))
+            loss = (O.masked_mse(out["rgb_map"], tgt, mask, COEF, sample_rays) + O.masked_mse(out["rgb0"], tgt, mask, COEF, sample_rays)
+                    + O.masked_mse(out["depth_map"], prior, mask, COEF, sample_rays, divisor=FAR)
+                    + O.masked_mse(out["depth0"], prior, mask, COEF, sample_rays, divisor=FAR))
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        with torch.no_grad():
+            out = O.render_rays(rays, pc, pf, ARCH, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, white_bkgd=True)
+        return float(out["rgb_map"].sum())
+
+    for w in range(warmup):
+        step(w)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        step(k)
+    dt = (time.perf_counter() - t0) / steps
+    val = sample_rays / dt
+    base = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_rays} rays/step x {steps} steps of workload A ({args.mode}), torch CPU fp32, {torch.get_num_threads()} threads"}
+    if quiet:
+        return base
+    line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"A: ({N_SAMPLES} coarse + {N_IMPORTANCE} fine), viewdirs, 8x256 coarse+fine MLPs, {args.mode}; "
+                                   f"bounded sample of {sample_rays} rays/step", "mode": args.mode},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", choices=["train", "render"], default="train")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        run_reference(args)
+        return
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

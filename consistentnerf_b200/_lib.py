@@ -75,11 +75,27 @@ def last_error() -> str:
     return buf.value.decode(errors="replace")
 
 
+# kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+launch_count = 0
+# name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
+event_trace = {}
+
+
 def call(name: str, *args):
     """Invoke an int-status entry point; non-zero status raises RuntimeError(last_error)."""
+    global launch_count
+    trace = event_trace.get(name)
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {last_error()}")
+    if trace is not None:
+        e1.record()
+        trace.append((e0, e1))
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
 
 
 def ptr(t):

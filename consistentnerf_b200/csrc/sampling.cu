@@ -121,14 +121,71 @@ __global__ void ray_points_kernel(const float* __restrict__ rays, int stride, co
 // ------------------------------------------------------------------------------------
 constexpr int kPdfWarps = 4;
 
+// ---- sum(weights + 1e-5) in the summation order of ATen's CPU sum kernel ---------------------------
+// The reference normalises the pdf with torch.sum(weights, -1) (NP/run_nerf_helpers.py:209).  Float
+// addition is not associative and the rounded total decides the low bits of every cdf entry, hence the
+// searchsorted indices at near-ties, so "bit-exact bin indices" needs a named summation order.  The
+// oracle device is the CPU; its kernel (aten/src/ATen/native/cpu/SumKernel.cpp: vectorized_inner_sum ->
+// row_sum -> multi_row_sum) adds 8-float vectors lane-wise with 4 interleaved accumulators and a
+// 16-step cascade, then the scalar tail, then the 8 lane partials in order.  This restates that order
+// (checked against torch.sum for every length 1..4095 in oracle/make_golden.py's container).
+constexpr int kAtenVec = 8;
+
+// row_sum over `size` elements x(i) = w[off + i*stride] + 1e-5, sequential on one thread
+__device__ float aten_row_sum(const float* __restrict__ w, int off, int stride, int size) {
+    auto X = [&](int i) { return __fadd_rn(w[off + i * stride], 1e-5f); };
+    const int size_ilp = size / 4;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+    int i = 0;
+    while (i + 16 <= size_ilp) {                      // level_step = 1 << max(4, CeilLog2(size)/4) = 16 for size < 2^20
+        for (int j = 0; j < 16; ++j, ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[0][k] = __fadd_rn(acc[0][k], X(4 * i + k));
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { acc[j][k] = __fadd_rn(acc[j][k], acc[j - 1][k]); acc[j - 1][k] = 0.f; }
+            if ((i & (15 << (4 * j))) != 0) break;
+        }
+    }
+    for (; i < size_ilp; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[0][k] = __fadd_rn(acc[0][k], X(4 * i + k));
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[0][k] = __fadd_rn(acc[0][k], acc[j][k]);
+    float p0 = acc[0][0];
+    for (int r = size_ilp * 4; r < size; ++r) p0 = __fadd_rn(p0, X(r));
+    p0 = __fadd_rn(p0, acc[0][1]); p0 = __fadd_rn(p0, acc[0][2]); p0 = __fadd_rn(p0, acc[0][3]);
+    return p0;
+}
+
+// whole-warp call; returns sum_j (w[j] + 1e-5) on every lane
+__device__ float aten_cpu_sum(const float* __restrict__ w, int n, int lane) {
+    float fin = 0.f;
+    if (n >= kAtenVec) {
+        const int vs = n / kAtenVec;
+        float part = lane < kAtenVec ? aten_row_sum(w, lane, kAtenVec, vs) : 0.f;
+        if (lane == 0) for (int k = vs * kAtenVec; k < n; ++k) fin = __fadd_rn(fin, __fadd_rn(w[k], 1e-5f));
+#pragma unroll
+        for (int j = 0; j < kAtenVec; ++j) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, part, j));
+    } else if (lane == 0) {
+        fin = aten_row_sum(w, 0, 1, n);
+    }
+    return __shfl_sync(0xffffffffu, fin, 0);
+}
+
 // Builds cdf[0..B-1] in shared memory from B-1 weights.  Follows sample_pdf
 // (NP/run_nerf_helpers.py:208-211): w += 1e-5; pdf = w / sum(w); cdf = [0, cumsum(pdf)].
-// The sum and the running cumsum are accumulated in double and rounded to fp32 per element,
-// which is what torch's CPU cumsum produces (hard part 3).
+// The running cumsum is accumulated in double and rounded to fp32 per element, which is what torch's
+// CPU cumsum produces (hard part 3); the total follows aten_cpu_sum above.
 __device__ void warp_build_cdf(const float* __restrict__ w, int nw, float* cdf_s, int lane) {
-    double part = 0.0;
-    for (int j = lane; j < nw; j += 32) part += (double)__fadd_rn(w[j], 1e-5f);
-    float total = (float)warp_sum(part);
+    float total = aten_cpu_sum(w, nw, lane);
     // contiguous chunk per lane -> sequential inside, exclusive scan across lanes
     int per = (nw + 31) / 32;
     int j0 = lane * per, j1 = min(j0 + per, nw);

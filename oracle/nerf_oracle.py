@@ -21,7 +21,7 @@ __all__ = [
     "posenc", "nerf_param_shapes", "make_params", "mlp_forward", "stratified_z",
     "ray_points", "composite", "sample_pdf", "merge_sorted", "render_rays",
     "pixel_rays", "ndc_warp", "pack_rays", "project_points", "gather_reference",
-    "reference_view_rays", "hard_mask_pair", "masked_mse", "mse_to_psnr",
+    "reference_view_rays", "hard_mask_pair", "masked_mse", "mse_to_psnr", "aten_cpu_sum_f32",
 ]
 
 
@@ -391,3 +391,57 @@ def masked_mse(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, coe
 def mse_to_psnr(x: torch.Tensor) -> torch.Tensor:
     """NP/run_nerf_helpers.py:10."""
     return -10.0 * torch.log(x) / math.log(10.0)
+
+
+# --------------------------------------------------------------------------------------
+# summation order of torch.sum on the CPU (what NP/run_nerf_helpers.py:209 executes on the oracle device)
+# --------------------------------------------------------------------------------------
+def aten_cpu_sum_f32(x: np.ndarray, vec: int = 8) -> np.float32:
+    """float32 sum of a contiguous row in the order of ATen's CPU kernel (SumKernel.cpp:
+    vectorized_inner_sum -> row_sum -> multi_row_sum): ``vec``-wide lane partials with four interleaved
+    accumulators and a 16-step cascade, then the scalar tail, then the lane partials in order.  K5 restates
+    this order on the GPU (csrc/sampling.cu: aten_cpu_sum) so that cdf low bits -- and with them the
+    searchsorted indices at near-ties -- equal the reference's.  Pure-Python loops: small cases only."""
+    f32 = np.float32
+    x = np.asarray(x, dtype=f32)
+
+    def row_sum(get, size):
+        size_ilp = size // 4
+        acc = [[f32(0)] * 4 for _ in range(4)]
+        i = 0
+        while i + 16 <= size_ilp:
+            for _ in range(16):
+                for k in range(4):
+                    acc[0][k] = f32(acc[0][k] + get(4 * i + k))
+                i += 1
+            for j in range(1, 4):
+                for k in range(4):
+                    acc[j][k] = f32(acc[j][k] + acc[j - 1][k])
+                    acc[j - 1][k] = f32(0)
+                if (i & (15 << (4 * j))) != 0:
+                    break
+        while i < size_ilp:
+            for k in range(4):
+                acc[0][k] = f32(acc[0][k] + get(4 * i + k))
+            i += 1
+        for j in range(1, 4):
+            for k in range(4):
+                acc[0][k] = f32(acc[0][k] + acc[j][k])
+        p0 = acc[0][0]
+        for r in range(size_ilp * 4, size):
+            p0 = f32(p0 + get(r))
+        for k in range(1, 4):
+            p0 = f32(p0 + acc[0][k])
+        return p0
+
+    n = x.shape[0]
+    if n < vec:
+        return row_sum(lambda i: x[i], n)
+    vs = n // vec
+    parts = [row_sum(lambda v, j=j: x[v * vec + j], vs) for j in range(vec)]
+    fin = f32(0)
+    for k in range(vs * vec, n):
+        fin = f32(fin + x[k])
+    for j in range(vec):
+        fin = f32(fin + parts[j])
+    return fin

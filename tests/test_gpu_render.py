@@ -1,0 +1,166 @@
+"""End-to-end parity of render / render_rays (the drop-in surface) against the reference's golden
+vectors and the fp64 oracle, plus training-mode gradients against the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import nerf_oracle as O
+from util import ARCH, assert_close, module_from_params, rel_err, workload_rays
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def cn():
+    import consistentnerf_b200 as m
+    return m
+
+
+def _kwargs(cn, coarse, fine, **over):
+    embed_fn, _ = cn.get_embedder(10, 0)
+    embeddirs_fn, _ = cn.get_embedder(4, 0)
+
+    def network_query_fn(inputs, viewdirs, network_fn):      # create_nerf's closure, NP/run_nerf_view.py:323-326
+        return cn.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn,
+                              netchunk=1024 * 64)
+    kw = dict(network_query_fn=network_query_fn, perturb=0.0, N_importance=128, network_fine=fine, N_samples=64,
+              network_fn=coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0.0, ndc=False, lindisp=False,
+              near=2.0, far=6.0)
+    kw.update(over)
+    return kw
+
+
+def _nets(g):
+    pc = O.make_params(int(g["seeds"][0]), sigma_bias=float(g["sigma_bias"]), **ARCH)
+    pf = O.make_params(int(g["seeds"][1]), sigma_bias=float(g["sigma_bias"]), **ARCH)
+    return pc, pf, module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+
+
+def test_render_deterministic_golden(cn):
+    g = load_golden("render_det")
+    pc, pf, coarse, fine = _nets(g)
+    rays = (t(g["rays_o"], device=DEV), t(g["rays_d"], device=DEV))
+    kw = _kwargs(cn, coarse, fine, near=float(g["near"]), far=float(g["far"]))
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = cn.render(40, 40, None, chunk=16, rays=rays, retraw=True, **kw)
+    got = dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, **extras)
+    for k in ("rgb_map", "acc_map", "depth_map", "rgb0", "acc0", "depth0", "z_std", "raw"):
+        assert_close(got[k], g[k], 1e-4, 1e-5, k)
+    assert_close(got["disp_map"], g["disp_map"], 2e-4, 1e-6, "disp_map")
+    # chunk invariance (batchify_rays contract, NP/run_nerf.py:79-80)
+    with torch.no_grad():
+        again = cn.render(40, 40, None, chunk=1024, rays=rays, retraw=True, **kw)
+    assert torch.equal(again[0], rgb) and torch.equal(again[3], depth)
+
+
+def test_render_stochastic_pytest_hook_golden(cn):
+    """perturb=1, raw_noise_std=1, lindisp, black background, under the reference's fixed-RNG hook."""
+    g = load_golden("render_pytest")
+    pc, pf, coarse, fine = _nets(g)
+    rays = (t(g["rays_o"], device=DEV), t(g["rays_d"], device=DEV))
+    kw = _kwargs(cn, coarse, fine, near=float(g["near"]), far=float(g["far"]), perturb=1.0, raw_noise_std=1.0,
+                 lindisp=True, white_bkgd=False, pytest=True)
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = cn.render(40, 40, None, chunk=1024, rays=rays, retraw=True, **kw)
+    got = dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, **extras)
+    for k in ("rgb_map", "acc_map", "depth_map", "rgb0", "acc0", "depth0", "z_std", "raw"):
+        assert_close(got[k], g[k], 1e-4, 1e-5, k)
+
+
+def test_vanilla_flavour_has_no_depth(cn):
+    g = load_golden("render_det")
+    pc, pf, coarse, fine = _nets(g)
+    api = cn.make_api(with_depth=False)
+    rays = (t(g["rays_o"], device=DEV), t(g["rays_d"], device=DEV))
+    with torch.no_grad():
+        out = api.render(40, 40, None, chunk=1024, rays=rays, **_kwargs(cn, coarse, fine))
+    assert len(out) == 4 and "depth0" not in out[3] and "rgb0" in out[3]
+    assert_close(out[0], g["rgb_map"], 1e-4, 1e-5)
+
+
+def test_render_workload_a_vs_fp64_oracle(cn):
+    """512 rays of the headline workload, judged against the fp64 restatement:
+    the candidate must be within 1e-4 (scale-relative) wherever the fp32 oracle itself is."""
+    n = 512
+    o, d = workload_rays(n)
+    pc = O.make_params(0, sigma_bias=0.5, **ARCH)
+    pf = O.make_params(1, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = cn.render(1, n, None, chunk=4096, rays=(o.to(DEV), d.to(DEV)),
+                                              **_kwargs(cn, coarse, fine))
+    rays64 = O.pack_rays(o.double(), d.double(), 2.0, 6.0, True)
+    ref = O.render_rays(rays64, {k: v.double() for k, v in pc.items()}, {k: v.double() for k, v in pf.items()}, ARCH,
+                        n_samples=64, n_importance=128, white_bkgd=True)
+    ref32 = O.render_rays(rays64.float(), pc, pf, ARCH, n_samples=64, n_importance=128, white_bkgd=True)
+    got = dict(rgb_map=rgb, acc_map=acc, depth_map=depth, rgb0=ex["rgb0"], depth0=ex["depth0"], acc0=ex["acc0"])
+    for k, v in got.items():
+        e, e32 = rel_err(v, ref[k]), rel_err(ref32[k], ref[k])
+        print(f"{k:10s} candidate {e:.2e}   fp32 oracle {e32:.2e}")
+        assert e < max(1e-4, 2 * e32), k
+
+
+def test_training_gradients_match_oracle_autograd(cn):
+    """loss = img2mse(rgb, tgt) + img2mse(rgb0, tgt) (NP/run_nerf.py:770-777), perturb + noise supplied
+    through the pytest hook so that oracle and kernels see identical random numbers."""
+    n = 96
+    o, d = workload_rays(n, seed=3)
+    pc = O.make_params(2, sigma_bias=0.5, **ARCH)
+    pf = O.make_params(3, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    tgt = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    kw = _kwargs(cn, coarse, fine, perturb=1.0, raw_noise_std=1.0, pytest=True)
+    rgb, disp, acc, depth, ex = cn.render(1, n, None, chunk=4096, rays=(o.to(DEV), d.to(DEV)), retraw=True, **kw)
+    loss = cn.img2mse(rgb, tgt.to(DEV)) + cn.img2mse(ex["rgb0"], tgt.to(DEV))
+    loss.backward()
+
+    np.random.seed(0); t_rand = torch.tensor(np.random.rand(n, 64))
+    np.random.seed(0); noise_c = torch.tensor(np.random.rand(n, 64))
+    np.random.seed(0); u = torch.tensor(np.random.rand(n, 128))
+    np.random.seed(0); noise_f = torch.tensor(np.random.rand(n, 192))
+    # the kernels consume fp32 random numbers: round the oracle's copies the same way
+    rnd = dict(t_rand=t_rand.float(), u=u.float(), noise_coarse=noise_c.float(), noise_fine=noise_f.float())
+
+    def oracle_grads(dt):
+        c = {k: v.to(dt).requires_grad_(True) for k, v in pc.items()}
+        f = {k: v.to(dt).requires_grad_(True) for k, v in pf.items()}
+        rays = O.pack_rays(o.to(dt), d.to(dt), 2.0, 6.0, True)
+        ref = O.render_rays(rays, c, f, ARCH, n_samples=64, n_importance=128, white_bkgd=True,
+                            **{k: v.to(dt) for k, v in rnd.items()})
+        ref_loss = ((ref["rgb_map"] - tgt.to(dt)) ** 2).mean() + ((ref["rgb0"] - tgt.to(dt)) ** 2).mean()
+        ref_loss.backward()
+        return float(ref_loss.detach()), c, f
+
+    loss64, c64, f64 = oracle_grads(torch.float64)
+    _, c32, f32 = oracle_grads(torch.float32)
+    assert abs(float(loss.detach()) - loss64) < 1e-4 * abs(loss64)
+    # Adjudication: the fp32 reference path itself is ~1e-3 away from fp64 on the early
+    # layers (fp32 sample positions amplified by the 2^9 octave), so the candidate is held to the 1e-4 bar or
+    # to twice the fp32 oracle's own distance from fp64, whichever is larger.
+    for net, p64, p32 in ((coarse, c64, c32), (fine, f64, f32)):
+        for name, prm in net.named_parameters():
+            if p64[name].grad is None:
+                assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
+                continue
+            cand, floor = rel_err(prm.grad, p64[name].grad), rel_err(p32[name].grad, p64[name].grad)
+            assert cand < max(1e-4, 2.0 * floor), (name, cand, floor)
+
+
+def test_whole_image_render_from_pose(cn):
+    """render(c2w=...) path of render_path (NP/run_nerf_view.py:270): rays generated on the device."""
+    H = W = 20
+    K = np.array([[25.0, 0, 10.0], [0, 25.0, 10.0], [0, 0, 1]], dtype=np.float32)
+    c2w = torch.tensor([[1.0, 0, 0, 0.1], [0, 1, 0, -0.2], [0, 0, 1, 4.0]])
+    pc = O.make_params(4, sigma_bias=0.5, **ARCH)
+    pf = O.make_params(5, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    with torch.no_grad():
+        rgb, disp, acc, depth, _ = cn.render(H, W, K, chunk=128, c2w=c2w.to(DEV), **_kwargs(cn, coarse, fine))
+    assert rgb.shape == (H, W, 3) and depth.shape == (H, W)
+    ro, rd = O.pixel_rays(H, W, K, c2w)
+    rays = O.pack_rays(ro.reshape(-1, 3), rd.reshape(-1, 3), 2.0, 6.0, True)
+    ref = O.render_rays(rays, pc, pf, ARCH, n_samples=64, n_importance=128, white_bkgd=True)
+    assert_close(rgb.reshape(-1, 3), ref["rgb_map"], 1e-4, 1e-5)
+    assert_close(depth.reshape(-1), ref["depth_map"], 1e-4, 1e-5)

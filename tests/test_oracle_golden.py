@@ -120,3 +120,17 @@ def test_masked_losses():
     close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], divisor=far, use_unmasked=False),
           g["depth_loss_masked_only"], rtol=1e-6)
     close(O.masked_mse(d, q, m, coef, n_ref=d.shape[0], divisor=far), g["depth_loss_both"], rtol=1e-6)
+
+
+def test_sum_order_restatement_matches_torch_cpu():
+    """K5's total is summed in ATen's CPU order; this pins the restatement of that order to torch.sum here."""
+    rs = np.random.RandomState(0)
+    for n in (1, 3, 7, 8, 9, 31, 61, 62, 63, 64, 127, 129, 255, 600, 1031):
+        X = (rs.rand(16, n) ** 3).astype(np.float32)
+        ref = torch.from_numpy(X).sum(-1, keepdim=True).numpy()[:, 0]
+        mine = np.array([O.aten_cpu_sum_f32(X[r]) for r in range(16)], dtype=np.float32)
+        assert np.array_equal(ref, mine), n
+    g = load_golden("sample_pdf")
+    w = (g["weights"] + np.float32(1e-5)).astype(np.float32)
+    tot = np.array([O.aten_cpu_sum_f32(r) for r in w], dtype=np.float32)
+    assert np.array_equal(tot, torch.from_numpy(w).sum(-1).numpy())
