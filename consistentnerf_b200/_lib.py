@@ -36,6 +36,11 @@ SIGNATURES = {
     "cnerf_weights_destroy": (None, [_P]),
     "cnerf_weights_refresh": (_I, [_P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_mlp_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "cnerf_mlp_acts_bytes": (c_int64, [c_int64]),
+    "cnerf_mlp_fwd_train": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "cnerf_mlp_grads_bytes": (c_int64, [c_int64]),
+    "cnerf_mlp_bwd_workspace_bytes": (c_int64, []),
+    "cnerf_mlp_bwd": (_I, [_P, _P, _P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cnerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
@@ -76,7 +81,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
-LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 3, "cnerf_mlp_bwd": 40, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
 launch_count = 0
 # name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
 event_trace = {}

@@ -1,0 +1,689 @@
+// K3b: backward of the canonical 8x256 NeRF MLP on tcgen05 tensor cores (sm_100a).
+//
+// Inputs: d_raw [P,4] (from the compositing backward), the activation records written by the training
+// forward (mlp_tc.cu, kSave), the live weights.  Three stages, all with the forward's fp16 hi/lo split
+// (3 MMAs per MAC, fp32 accumulation in TMEM):
+//
+//   1. mlp_bwd_data_kernel   the data-gradient chain, fused over the layers like the forward: per 128-point
+//      tile G9 = (d_rgb W_rgb) * [hv>0]  ->  G8 = G9 W9[:, :256]  ->  G7 = (G8 W8 + d_sigma w_alpha) * [h7>0]
+//      ->  G_{l-1} = (G_l W_l) * [h_{l-1}>0] ... down to G0.  G_l is the gradient w.r.t. the pre-activation of
+//      layer l; every G_l tile is streamed to HBM as the next stage's operand.  Transposed weight blocks come
+//      through the same cp.async.bulk ring as in the forward.
+//   2. mlp_bwd_weight_kernel dW_l = G_l^T X_l as a GEMM whose reduction dimension is the points: both operands
+//      are read back as MN-major UMMA operands (the record layout is valid for both majors), accumulators stay
+//      in TMEM over all tiles of a CTA, one partial per CTA, deterministic reduction.  Spare warps sum the bias
+//      gradients from the same shared-memory tiles.
+//   3. mlp_heads_grad_kernel the two narrow heads (alpha_linear 256->1, rgb_linear 128->3) in fp32 on CUDA cores.
+//
+// Gradients are tiny (mean losses over thousands of rays), so G is carried times a power-of-two scale derived
+// on the device from max|d_raw| (no host sync); the final reductions multiply by its exact inverse.
+#include "mlp_layout.cuh"
+#include <vector>
+
+namespace cnerf {
+
+// gradient record per 128-point tile: G9 (K=128: [hi 32K | lo 32K]) then G8, G7, ..., G0 (128 KB each)
+__host__ __device__ constexpr size_t g_slot(int l) { return l == 9 ? 0 : 65536 + (size_t)(8 - l) * 131072; }
+constexpr size_t kGTileBytes = 65536 + 9 * 131072;     // 1 245 184 B
+
+// workspace map (bytes)
+constexpr size_t kWsAmax = 0;                                           // uint32: bits of max|d_raw|
+constexpr size_t kWsDwPart = 256;                                       // [148][128 x 512] fp32
+constexpr size_t kWsDbPart = kWsDwPart + (size_t)kNumSMs * 128 * 512 * 4;   // [148][2][256] fp32
+constexpr size_t kWsHeadPart = kWsDbPart + (size_t)kNumSMs * 2 * 256 * 4;   // [148][kHeadFloats] fp32
+constexpr int kHeadFloats = 384 + 256 + 4;                              // dW_rgb, dW_alpha, db_rgb(3)+db_alpha
+constexpr size_t kWsBytes = kWsHeadPart + (size_t)kNumSMs * kHeadFloats * 4 + 256;
+
+constexpr float kGradTarget = 256.f;                                    // max|d_raw| is scaled to [128, 256]
+
+__device__ __forceinline__ float grad_scale(const uint32_t* amax_bits) {
+    float amax = __uint_as_float(*amax_bits);
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) return 1.f;
+    return exp2f(floorf(log2f(kGradTarget / amax)));
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = fabsf(x[i]);
+        if (v < 3.0e38f) m = fmaxf(m, v);              // ignore inf / nan
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
+
+// ------------------------------------------------------------------------------------
+// transposed weight stream for the data-gradient chain
+// ------------------------------------------------------------------------------------
+struct BwdBlk { uint8_t step, half, a_kg, first, last_of_step, wait_a, kb, pad; };   // step s <-> layer 9 - s
+__constant__ BwdBlk c_bwd_blocks[kMaxBlocks];
+__constant__ int c_num_bwd_blocks;
+
+static std::vector<BwdBlk> build_bwd_program() {
+    std::vector<BwdBlk> prog;
+    for (int step = 0; step < 9; ++step) {
+        int kblocks = step == 0 ? 4 : 8;               // G9 is 128 wide, the others 256
+        for (int h = 0; h < 2; ++h)
+            for (int kb = 0; kb < kblocks; ++kb) {
+                BwdBlk b = {};
+                b.step = (uint8_t)step; b.half = (uint8_t)h; b.a_kg = (uint8_t)(4 * kb); b.kb = (uint8_t)kb;
+                b.first = kb == 0; b.last_of_step = (h == 1 && kb + 1 == kblocks); b.wait_a = (h == 0 && kb == 0);
+                prog.push_back(b);
+            }
+    }
+    return prog;
+}
+
+// block (step, half, kb): B[r][k] = W_L[kb*32 + k][col0 + half*128 + r],  L = 9 - step, col0 = 63 for the skip layer
+__global__ void __launch_bounds__(256)
+pack_bwd_weights_kernel(RawParams p, uint8_t* __restrict__ stream) {
+    BwdBlk bi = c_bwd_blocks[blockIdx.x];
+    const int L = 9 - bi.step;
+    const float* W = p.w[L];
+    const int ld = p.ld[L], col0 = (L == 5) ? 63 : 0;
+    uint8_t* dst = stream + (size_t)blockIdx.x * kBlockBytes;
+    for (int u = threadIdx.x; u < 512; u += 256) {
+        int r = u & 127, kg = u >> 7;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = W[(size_t)(bi.kb * 32 + kg * 8 + e) * ld + col0 + bi.half * 128 + r];
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_pack2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+        size_t off = (size_t)kg * kLBO + (size_t)r * 16;
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dst + kBlockHalfBytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+// ------------------------------------------------------------------------------------
+// 1. data-gradient chain
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_bwd_data_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
+                    const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
+                    uint8_t* __restrict__ grads) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kBars, bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_a = bar_empty + 8 * kStages, bar_d = bar_a + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kTmemSlot);
+    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+    const int nblk = c_num_bwd_blocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, kEpiThreads);
+        mbar_init(bar_d, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(sbase + kTmemSlot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== weight loader =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int b = 0; b < nblk; ++b, ++it) {
+                    uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
+                    bulk_g2s(sbase + kRing + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
+                }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (also streams every finished G tile to HBM) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(128, 128);
+            uint32_t it = 0, a_cnt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                uint8_t* rec = grads + (size_t)tile * kGTileBytes;
+                for (int b = 0; b < nblk; ++b, ++it) {
+                    BwdBlk bi = c_bwd_blocks[b];
+                    if (bi.wait_a) {
+                        mbar_wait(bar_a, a_cnt & 1); ++a_cnt; tc_fence_after();
+                        if (bi.step == 0) {
+                            bulk_s2g(rec, sbase + kActHi, 32768);
+                            bulk_s2g(rec + 32768, sbase + kActLo, 32768);
+                        } else {
+                            bulk_s2g(rec + g_slot(9 - bi.step), sbase + kActHi, 131072);
+                        }
+                        bulk_commit();
+                    }
+                    uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    uint32_t a_hi = sbase + kActHi + bi.a_kg * kLBO, a_lo = sbase + kActLo + bi.a_kg * kLBO;
+                    uint32_t b_hi = sbase + kRing + s * kBlockBytes, b_lo = b_hi + kBlockHalfBytes;
+                    uint32_t d = tmem + bi.half * 128;
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 2; ++ks) {
+                        uint64_t ah = smem_desc(a_hi + ks * 2 * kLBO), al = smem_desc(a_lo + ks * 2 * kLBO);
+                        uint64_t bh = smem_desc(b_hi + ks * 2 * kLBO), bl = smem_desc(b_lo + ks * 2 * kLBO);
+                        umma_f16(d, ah, bh, idesc, (bi.first && ks == 0) ? 0u : 1u);
+                        umma_f16(d, ah, bl, idesc, 1u);
+                        umma_f16(d, al, bh, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                    if (bi.last_of_step) { bulk_wait_read0(); umma_commit(bar_d); }
+                }
+                mbar_wait(bar_a, a_cnt & 1); ++a_cnt;            // G0 written by the last epilogue
+                bulk_s2g(rec + g_slot(0), sbase + kActHi, 131072);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            bulk_wait0();
+        }
+    } else {
+        // ===== prologue + epilogue warps =====
+        const int e = warp;
+        const uint32_t row = (uint32_t)((e & 3) * 32 + lane);
+        const int part = e >> 2;
+        const uint32_t t_lane = tmem + ((uint32_t)((e & 3) * 32) << 16);
+        const float scale = grad_scale(amax_bits);
+        uint32_t d_cnt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int grow = tile * (int)kRows + (int)row;
+            const bool valid = grow < n_points;
+            const uint8_t* arec = acts + (size_t)tile * kTileBytes;
+            float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
+            dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+            {   // G9 = (d_rgb W_rgb) * [hv > 0], 64 columns per thread
+                const uint8_t* hv = arec + kSlotHV;               // hi part: 16 k-groups
+#pragma unroll 1
+                for (int g = 0; g < 8; ++g) {
+                    const int kg = part * 8 + g, c = kg * 8;
+                    uint4 m = __ldg(reinterpret_cast<const uint4*>(hv + (size_t)kg * 2048 + row * 16));
+                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float gsum = dr.x * __ldg(misc + kMiscRgbW + c + j) + dr.y * __ldg(misc + kMiscRgbW + 128 + c + j) +
+                                     dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
+                        uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
+                        v[j] = hb ? clamp_h(gsum) : 0.f;
+                    }
+                    store_split8(sbase + kActHi, sbase + kActLo, row, kg, v);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+            }
+            for (int step = 0; step < 9; ++step) {
+                mbar_wait(bar_d, d_cnt & 1); ++d_cnt;
+                tc_fence_after();
+                const int L = 9 - step;                           // D = gradient w.r.t. the input of layer L
+                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;   // ReLU mask of that input (L <= 8)
+                const uint32_t col0 = (uint32_t)part * 128;
+#pragma unroll 1
+                for (uint32_t ch = 0; ch < 4; ++ch) {
+                    const uint32_t c = col0 + ch * 32;
+                    uint4 m[4];
+                    if (L != 9) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            m[g] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)((c >> 3) + g) * 2048 + row * 16));
+                    }
+                    float v[32];
+                    tmem_ld32(t_lane + c, v);
+                    tmem_ld_wait();
+                    if (L == 8) {                                 // + d_sigma * alpha_linear.weight
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 aw = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + j));
+                            v[j] = fmaf(dr.w, aw.x, v[j]); v[j + 1] = fmaf(dr.w, aw.y, v[j + 1]);
+                            v[j + 2] = fmaf(dr.w, aw.z, v[j + 2]); v[j + 3] = fmaf(dr.w, aw.w, v[j + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (L != 9) {
+                            const uint32_t mw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
+                                v[8 * g + j] = hb ? clamp_h(v[8 * g + j]) : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 * g + j] = clamp_h(v[8 * g + j]);
+                        }
+                        store_split8(sbase + kActHi, sbase + kActLo, row, (c >> 3) + g, v + 8 * g);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------
+// 2. weight gradients: D[n_out, k_in] = sum_p G[p, n_out] X[p, k_in]
+// ------------------------------------------------------------------------------------
+struct DwSrc { uint32_t slot_off, kgroups, lo_off; };        // hi k-groups at slot_off, lo k-groups at slot_off + lo_off
+struct DwPass {
+    int n_a, n_x;
+    DwSrc a[2];            // G sources in the gradient record (kgroups 32 -> two 128-row halves, 16 -> one)
+    DwSrc x[2];            // X sources in the activation record (N = 8 * kgroups)
+    int db_mask;           // bit i: sum bias gradient of a[i]
+};
+
+constexpr int kDwStages = 3;
+constexpr uint32_t kDwStageBytes = 73728;                     // 72 KB: two 256-wide G quarters + the 64-wide encoding
+constexpr uint32_t kDwBars = kDwStages * kDwStageBytes;       // 221184
+constexpr uint32_t kDwSmem = kDwBars + 128;
+constexpr int kDwThreads = 320;                               // 8 reduction/epilogue warps, loader warp, MMA warp
+constexpr uint32_t kQuarter = 512;                            // bytes of one k-group for 32 points
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+mlp_bwd_weight_kernel(DwPass P, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ grads, int num_tiles,
+                      float* __restrict__ dw_part, float* __restrict__ db_part) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwStages, bar_acc = bar_empty + 8 * kDwStages;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kDwBars + 96);
+
+    // contiguous tile range of this CTA
+    const int per = num_tiles / gridDim.x, rem = num_tiles % gridDim.x;
+    const int t0 = blockIdx.x * per + min((int)blockIdx.x, rem), t1 = t0 + per + ((int)blockIdx.x < rem ? 1 : 0);
+    const int n_stage_iters = (t1 - t0) * 4;
+
+    // stage map: A sources then X sources, each [hi kgroups*512 | lo kgroups*512]
+    uint32_t a_off[2], x_off[2], off = 0;
+    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += 2 * P.a[i].kgroups * kQuarter; }
+    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += 2 * P.x[j].kgroups * kQuarter; }
+    const uint32_t stage_bytes = off;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kDwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 9); }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(sbase + kDwBars + 96, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== loader: per (tile, quarter) one stage; every k-group quarter is a 512-byte bulk copy =====
+        for (int it = 0; it < n_stage_iters; ++it) {
+            const int tile = t0 + (it >> 2), q = it & 3;
+            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+            if (lane == 0) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+            }
+            __syncwarp();
+            const uint32_t dst0 = sbase + s * kDwStageBytes;
+            for (int i = 0; i < P.n_a + P.n_x; ++i) {
+                const bool is_a = i < P.n_a;
+                const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
+                const uint8_t* g = (is_a ? grads + (size_t)tile * kGTileBytes : acts + (size_t)tile * kTileBytes) + src.slot_off + q * kQuarter;
+                const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
+                for (uint32_t c = lane; c < 2 * src.kgroups; c += 32) {    // c < kgroups: hi k-group c, else lo k-group c - kgroups
+                    const size_t so = c < src.kgroups ? (size_t)c * 2048 : (size_t)src.lo_off + (size_t)(c - src.kgroups) * 2048;
+                    bulk_g2s(d + c * kQuarter, g + so, kQuarter, bar_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int it = 0; it < n_stage_iters; ++it) {
+                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = sbase + s * kDwStageBytes;
+#pragma unroll 1
+                for (uint32_t ks = 0; ks < 2; ++ks) {
+                    uint32_t col = 0;
+                    for (int i = 0; i < P.n_a; ++i) {
+                        const uint32_t halves = P.a[i].kgroups / 16, a_lo_off = P.a[i].kgroups * kQuarter;
+                        for (uint32_t h = 0; h < halves; ++h) {
+                            const uint32_t a_hi = st + a_off[i] + h * 16 * kQuarter + ks * 256;
+                            const uint64_t ah = smem_desc_any(a_hi, 128, kQuarter), al = smem_desc_any(a_hi + a_lo_off, 128, kQuarter);
+                            for (int j = 0; j < P.n_x; ++j) {
+                                const uint32_t N = P.x[j].kgroups * 8;
+                                const uint32_t x_hi = st + x_off[j] + ks * 256;
+                                const uint64_t xh = smem_desc_any(x_hi, 128, kQuarter), xl = smem_desc_any(x_hi + P.x[j].kgroups * kQuarter, 128, kQuarter);
+                                const uint32_t idesc = instr_desc_mn(128, N);
+                                umma_f16(tmem + col, ah, xh, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+                                umma_f16(tmem + col, ah, xl, idesc, 1u);
+                                umma_f16(tmem + col, al, xh, idesc, 1u);
+                                col += N;
+                            }
+                        }
+                    }
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_acc);
+        }
+    } else {
+        // ===== bias-gradient column sums (from the same SMEM tiles), then the TMEM -> partial epilogue =====
+        float acc[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
+        for (int it = 0; it < n_stage_iters; ++it) {
+            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            const uint32_t st = sbase + s * kDwStageBytes;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i < P.n_a && ((P.db_mask >> i) & 1)) {
+                    const uint32_t per_warp = P.a[i].kgroups / 8;       // 4 (256 wide) or 2 (128 wide)
+#pragma unroll
+                    for (uint32_t g = 0; g < 4; ++g) {
+                        if (g < per_warp) {
+                            const uint32_t kg = warp * per_warp + g;
+                            const uint32_t addr = st + a_off[i] + kg * kQuarter + lane * 16;
+                            uint4 hi, lo;
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(addr));
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * kQuarter));
+                            const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                                float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                                acc[i][g * 8 + 2 * e] += a.x + b.x;
+                                acc[i][g * 8 + 2 * e + 1] += a.y + b.y;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        }
+        // bias partials: reduce over the 32 point-lanes
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i < P.n_a && ((P.db_mask >> i) & 1)) {
+                const uint32_t per_warp = P.a[i].kgroups / 8;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    float v = warp_sum(acc[i][k]);
+                    if (lane == 0 && (uint32_t)(k >> 3) < per_warp)
+                        db_part[((size_t)blockIdx.x * 2 + i) * 256 + (warp * per_warp + (k >> 3)) * 8 + (k & 7)] = v;
+                }
+            }
+        }
+        // accumulators -> per-CTA partial, block by block: [block][128 rows][N]
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        float* part = dw_part + (size_t)blockIdx.x * 128 * 512;
+        const uint32_t rowq = (uint32_t)(warp & 3) * 32, row = rowq + lane;
+        uint32_t col = 0;
+        for (int i = 0; i < P.n_a; ++i)
+            for (uint32_t h = 0; h < P.a[i].kgroups / 16; ++h)
+                for (int j = 0; j < P.n_x; ++j) {
+                    const uint32_t N = P.x[j].kgroups * 8;
+                    float* blk = part + (size_t)col * 128;                 // block base: 128 x N floats
+                    for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < N; c += 64) {
+                        float v[32];
+                        tmem_ld32(tmem + (rowq << 16) + col + c, v);
+                        tmem_ld_wait();
+                        float4* o = reinterpret_cast<float4*>(blk + (size_t)row * N + c);
+                        if (n_stage_iters == 0) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    }
+                    col += N;
+                }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+// dst[(row0 + r) * ld + col0 + c] (+)= inv_scale * sum_cta part[cta][blk_off + r * blk_n + src_col0 + c]
+struct DwSeg { float* dst; int ld, row0, col0, ncols, blk_off, blk_n, src_col0; };
+struct DwSegs { int n; DwSeg s[6]; };
+
+__global__ void dw_reduce_kernel(DwSegs S, const float* __restrict__ part, int n_cta, const uint32_t* __restrict__ amax_bits,
+                                 int accumulate) {
+    const DwSeg sg = S.s[blockIdx.y];
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * sg.ncols) return;
+    int r = idx / sg.ncols, c = idx - r * sg.ncols;
+    const float* p = part + sg.blk_off + (size_t)r * sg.blk_n + sg.src_col0 + c;
+    float acc = 0.f;
+    for (int k = 0; k < n_cta; ++k) acc += p[(size_t)k * 128 * 512];
+    acc *= 1.f / grad_scale(amax_bits);
+    float* d = sg.dst + (size_t)(sg.row0 + r) * sg.ld + sg.col0 + c;
+    *d = accumulate ? *d + acc : acc;
+}
+
+__global__ void db_reduce_kernel(float* __restrict__ dst, int n, const float* __restrict__ db_part, int src, int n_cta,
+                                 const uint32_t* __restrict__ amax_bits, int accumulate) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float acc = 0.f;
+    for (int k = 0; k < n_cta; ++k) acc += db_part[((size_t)k * 2 + src) * 256 + c];
+    acc *= 1.f / grad_scale(amax_bits);
+    dst[c] = accumulate ? dst[c] + acc : acc;
+}
+
+// ------------------------------------------------------------------------------------
+// 3. narrow heads in fp32: dW_rgb[ch][n] = sum d_rgb[p][ch] hv[p][n], dW_alpha[k] = sum d_sigma[p] h7[p][k]
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_hilo8(const uint8_t* hi_ptr, size_t lo_off, float* out) {
+    uint4 hi = __ldg(reinterpret_cast<const uint4*>(hi_ptr));
+    uint4 lo = __ldg(reinterpret_cast<const uint4*>(hi_ptr + lo_off));
+    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+        out[2 * e] = a.x + b.x; out[2 * e + 1] = a.y + b.y;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mlp_heads_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict__ acts, int n_points, float* __restrict__ part) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (n_points + 127) / 128;
+    float rgb[3][16], al[32], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) rgb[0][k] = rgb[1][k] = rgb[2][k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) al[k] = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint8_t* rec = acts + (size_t)tile * kTileBytes;
+        for (int rg = 0; rg < 4; ++rg) {
+            const int row = rg * 32 + lane, grow = tile * 128 + row;
+            float4 dr = grow < n_points ? __ldg(reinterpret_cast<const float4*>(d_raw) + grow) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp == 0) { bsum[0] += dr.x; bsum[1] += dr.y; bsum[2] += dr.z; bsum[3] += dr.w; }
+            float v[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {                     // hv: 16 k-groups, two per warp
+                load_hilo8(rec + kSlotHV + (size_t)(warp * 2 + g) * 2048 + row * 16, 32768, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    rgb[0][g * 8 + e] = fmaf(dr.x, v[e], rgb[0][g * 8 + e]);
+                    rgb[1][g * 8 + e] = fmaf(dr.y, v[e], rgb[1][g * 8 + e]);
+                    rgb[2][g * 8 + e] = fmaf(dr.z, v[e], rgb[2][g * 8 + e]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                     // h7: 32 k-groups, four per warp
+                load_hilo8(rec + kSlotH0 + 7 * 131072 + (size_t)(warp * 4 + g) * 2048 + row * 16, 65536, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) al[g * 8 + e] = fmaf(dr.w, v[e], al[g * 8 + e]);
+            }
+        }
+    }
+    float* out = part + (size_t)blockIdx.x * kHeadFloats;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float v = warp_sum(rgb[ch][k]);
+            if (lane == 0) out[ch * 128 + warp * 16 + k] = v;
+        }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        float v = warp_sum(al[k]);
+        if (lane == 0) out[384 + warp * 32 + k] = v;
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = warp_sum(bsum[k]);
+            if (lane == 0) out[640 + k] = v;
+        }
+    }
+}
+
+__global__ void heads_reduce_kernel(const float* __restrict__ part, int n_cta, float* __restrict__ d_rgb_w,
+                                    float* __restrict__ d_rgb_b, float* __restrict__ d_alpha_w, float* __restrict__ d_alpha_b,
+                                    int accumulate) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kHeadFloats) return;
+    float acc = 0.f;
+    for (int k = 0; k < n_cta; ++k) acc += part[(size_t)k * kHeadFloats + i];
+    float* d = i < 384 ? d_rgb_w + i : i < 640 ? d_alpha_w + (i - 384) : i < 643 ? d_rgb_b + (i - 640) : d_alpha_b;
+    *d = accumulate ? *d + acc : acc;
+}
+
+}  // namespace cnerf
+
+using namespace cnerf;
+
+// defined in mlp_tc.cu
+namespace cnerf { int upload_bwd_program_once(int* nblocks); }
+
+static int g_bwd_blocks = -1;
+int cnerf::upload_bwd_program_once(int* nblocks) {
+    if (g_bwd_blocks < 0) {
+        std::vector<BwdBlk> prog = build_bwd_program();
+        if ((int)prog.size() > kMaxBlocks) return set_error(CNERF_EINVAL, "backward program too long");
+        int n = (int)prog.size();
+        cudaError_t e = cudaMemcpyToSymbol(c_bwd_blocks, prog.data(), prog.size() * sizeof(BwdBlk));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_num_bwd_blocks, &n, sizeof(int));
+        if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_bwd_blocks)");
+        g_bwd_blocks = n;
+    }
+    *nblocks = g_bwd_blocks;
+    return CNERF_OK;
+}
+
+// called from cnerf_weights_refresh (mlp_tc.cu)
+namespace cnerf {
+int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaStream_t st) {
+    pack_bwd_weights_kernel<<<nblocks, 256, 0, st>>>(p, stream_bwd);
+    CNERF_LAUNCH_CHECK("pack_bwd_weights_kernel");
+    return CNERF_OK;
+}
+}  // namespace cnerf
+
+extern "C" int64_t cnerf_mlp_grads_bytes(int64_t n_points) { return ceil_div64(n_points, kRows) * (int64_t)kGTileBytes; }
+extern "C" int64_t cnerf_mlp_bwd_workspace_bytes(void) { return (int64_t)kWsBytes; }
+
+extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
+                             float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
+                             float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
+                             float* d_rgb_b, int accumulate, void* workspace, void* stream) {
+    CNERF_REQUIRE(w && w->packed && w->stream_bwd, "cnerf_mlp_bwd: weights handle not packed");
+    CNERF_REQUIRE(d_raw && acts && grads_rec && workspace && d_pts_w && d_pts_b && d_feature_w && d_feature_b && d_alpha_w &&
+                      d_alpha_b && d_views_w && d_views_b && d_rgb_w && d_rgb_b, "cnerf_mlp_bwd: null pointer");
+    CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd: negative n_points");
+    for (int i = 0; i < 8; ++i) CNERF_REQUIRE(d_pts_w[i] && d_pts_b[i], "cnerf_mlp_bwd: null pts_linears.%d gradient", i);
+    if (n_points == 0) return CNERF_OK;
+    cudaStream_t st = as_stream(stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
+        attr_set = true;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    uint32_t* amax = reinterpret_cast<uint32_t*>(ws + kWsAmax);
+    float* dw_part = reinterpret_cast<float*>(ws + kWsDwPart);
+    float* db_part = reinterpret_cast<float*>(ws + kWsDbPart);
+    float* head_part = reinterpret_cast<float*>(ws + kWsHeadPart);
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(acts);
+    uint8_t* g = reinterpret_cast<uint8_t*>(grads_rec);
+    const int tiles = ceil_div(n_points, (int)kRows);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+
+    cudaError_t e = cudaMemsetAsync(amax, 0, 4, st);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
+    absmax_kernel<<<kNumSMs, 256, 0, st>>>(d_raw, (int64_t)n_points * 4, amax);
+    CNERF_LAUNCH_CHECK("absmax_kernel");
+
+    mlp_bwd_data_kernel<<<grid, kThreads, kSmemTotal, st>>>(w->stream_bwd, w->misc, d_raw, a, amax, n_points, g);
+    CNERF_LAUNCH_CHECK("mlp_bwd_data_kernel");
+
+    mlp_heads_grad_kernel<<<grid, 256, 0, st>>>(d_raw, a, n_points, head_part);
+    CNERF_LAUNCH_CHECK("mlp_heads_grad_kernel");
+    heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, st>>>(head_part, grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
+    CNERF_LAUNCH_CHECK("heads_reduce_kernel");
+
+    // weight-gradient passes
+    auto H = [](int l) { return (uint32_t)(kSlotH0 + (size_t)l * 131072); };
+    auto run_pass = [&](const DwPass& P, const DwSegs& S, float* db0, int n0, float* db1, int n1) -> int {
+        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(P, a, g, tiles, dw_part, db_part);
+        CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
+        int maxc = 0;
+        for (int i = 0; i < S.n; ++i) maxc = S.s[i].ncols > maxc ? S.s[i].ncols : maxc;
+        dw_reduce_kernel<<<dim3(ceil_div(128 * maxc, 256), S.n), 256, 0, st>>>(S, dw_part, grid, amax, accumulate);
+        CNERF_LAUNCH_CHECK("dw_reduce_kernel");
+        if (db0) { db_reduce_kernel<<<ceil_div(n0, 256), 256, 0, st>>>(db0, n0, db_part, 0, grid, amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
+        if (db1) { db_reduce_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(db1, n1, db_part, 1, grid, amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
+        return CNERF_OK;
+    };
+    int rc;
+    {   // encoding pass: dW0 = G0^T E, dW5[:, :63] = G5^T E
+        DwPass P = {}; P.n_a = 2; P.n_x = 1; P.db_mask = 3;
+        P.a[0] = {(uint32_t)g_slot(0), 32, 65536}; P.a[1] = {(uint32_t)g_slot(5), 32, 65536}; P.x[0] = {(uint32_t)kSlotE, 8, 16384};
+        DwSegs S = {}; S.n = 4;
+        S.s[0] = {d_pts_w[0], 63, 0, 0, 63, 0 * 128 * 64, 64, 0};
+        S.s[1] = {d_pts_w[0], 63, 128, 0, 63, 1 * 128 * 64, 64, 0};
+        S.s[2] = {d_pts_w[5], 319, 0, 0, 63, 2 * 128 * 64, 64, 0};
+        S.s[3] = {d_pts_w[5], 319, 128, 0, 63, 3 * 128 * 64, 64, 0};
+        if ((rc = run_pass(P, S, d_pts_b[0], 256, d_pts_b[5], 256)) != CNERF_OK) return rc;
+    }
+    for (int l = 1; l <= 8; ++l) {   // 256-wide hidden inputs: layers 1..7 (layer 5: the h4 columns) and feature_linear (l == 8)
+        DwPass P = {}; P.n_a = 1; P.n_x = 1; P.db_mask = (l == 5) ? 0 : 1;
+        P.a[0] = {(uint32_t)g_slot(l), 32, 65536}; P.x[0] = {H(l - 1), 32, 65536};
+        float* dst = l == 8 ? d_feature_w : d_pts_w[l];
+        const int ld = l == 5 ? 319 : 256, c0 = l == 5 ? 63 : 0;
+        DwSegs S = {}; S.n = 2;
+        S.s[0] = {dst, ld, 0, c0, 256, 0, 256, 0};
+        S.s[1] = {dst, ld, 128, c0, 256, 128 * 256, 256, 0};
+        float* db = l == 5 ? nullptr : (l == 8 ? d_feature_b : d_pts_b[l]);
+        if ((rc = run_pass(P, S, db, 256, nullptr, 0)) != CNERF_OK) return rc;
+    }
+    {   // views_linears.0: X = [feature (256), direction encoding (27 of 32)]
+        DwPass P = {}; P.n_a = 1; P.n_x = 2; P.db_mask = 1;
+        P.a[0] = {(uint32_t)g_slot(9), 16, 32768}; P.x[0] = {(uint32_t)kSlotF, 32, 65536}; P.x[1] = {(uint32_t)kSlotV, 4, 16384};
+        DwSegs S = {}; S.n = 2;
+        S.s[0] = {d_views_w, 283, 0, 0, 256, 0, 256, 0};
+        S.s[1] = {d_views_w, 283, 0, 256, 27, 128 * 256, 32, 0};
+        if ((rc = run_pass(P, S, d_views_b, 128, nullptr, 0)) != CNERF_OK) return rc;
+    }
+    return CNERF_OK;
+}

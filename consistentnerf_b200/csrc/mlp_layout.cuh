@@ -1,0 +1,65 @@
+// Layout shared by the tensor-core MLP kernels: shared-memory map, activation-record slots, the fp32
+// side-parameter block and the weight handle.
+#pragma once
+#include "umma.cuh"
+
+namespace cnerf {
+
+constexpr int kNumLayers = 10;                  // 0-7 pts_linears, 8 feature_linear, 9 views_linears.0
+constexpr int kMaxBlocks = 160;
+constexpr uint32_t kBlockBytes = 16384;
+constexpr uint32_t kBlockHalfBytes = 8192;
+
+// misc fp32 parameter block
+constexpr int kMiscBias = 0;                    // [10][256]
+constexpr int kMiscAlphaW = 2560;               // [256]
+constexpr int kMiscAlphaB = 2816;               // [1]
+constexpr int kMiscRgbW = 2820;                 // [3][128]
+constexpr int kMiscRgbB = 3204;                 // [3]
+constexpr int kMiscFloats = 3208;
+
+struct RawParams {
+    const float* w[kNumLayers];
+    const float* b[kNumLayers];
+    const float* alpha_w; const float* alpha_b; const float* rgb_w; const float* rgb_b;
+    int ld[kNumLayers];
+};
+
+// ------------------------------------------------------------------------------------
+// shared-memory map of the fused kernel
+// ------------------------------------------------------------------------------------
+constexpr uint32_t kActHi = 0;                          // 32 k-groups x 2048 B  (K = 256)
+constexpr uint32_t kActLo = 65536;
+constexpr uint32_t kEmbHi = 131072;                     // 8 k-groups (K = 64): point encoding, later dir encoding
+constexpr uint32_t kEmbLo = 147456;
+constexpr uint32_t kRing = 163840;                      // 4 stages x 16 KB
+constexpr int kStages = 4;
+constexpr uint32_t kBars = kRing + kStages * kBlockBytes;      // 229376
+constexpr uint32_t kTmemSlot = kBars + 96;
+constexpr uint32_t kSAlpha = kBars + 128;               // float[128]
+constexpr uint32_t kSRgb = kSAlpha + 512;               // float[3][128]
+constexpr uint32_t kSmemTotal = kSRgb + 1536;           // 231552 <= 232448
+
+constexpr size_t kSlotE = 0, kSlotH0 = 32768, kSlotF = kSlotH0 + 8 * 131072, kSlotV = kSlotF + 131072,
+                 kSlotHV = kSlotV + 32768, kTileBytes = kSlotHV + 65536;      // 1 310 720 B per 128 points
+
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = kEpiThreads + 64;
+constexpr uint32_t kTmemCols = 512;
+
+// Training mode: every A operand (encodings and post-activation layer outputs, fp16 hi/lo in the UMMA
+// layout) is also streamed to HBM, one record per 128-point tile; the backward kernels (mlp_bwd_tc.cu)
+// read ReLU masks and dW operands from it.  Slot = [hi | lo], each k-group 2048 B (128 rows x 16 B).
+//   E  point encoding (K=64)   H0..H7 pts_linears outputs (K=256)   F feature_linear output (K=256)
+//   V  direction encoding (K=32 used, stored as the 64-wide buffer)  HV views_linears output (K=128)
+
+}  // namespace cnerf
+
+struct cnerf_weights {
+    uint8_t* stream = nullptr;      // forward weight stream: packed fp16 hi/lo blocks in program order
+    uint8_t* stream_bwd = nullptr;  // transposed blocks in the order the data-gradient chain consumes them
+    float* misc = nullptr;          // biases + alpha/rgb heads (fp32)
+    int num_blocks = 0, num_blocks_bwd = 0;
+    int device = -1;
+    bool packed = false;
+};

@@ -22,134 +22,15 @@
 // 128 contiguous bytes; element (row r, k) lives at  (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2  with
 // SBO = 128 B and LBO = rows*16 B = 2048 B for 128 rows.  A thread that owns a row writes 8
 // consecutive k as one 16-byte store, and a warp's 32 rows are 512 contiguous bytes: conflict free.
-#include "common.cuh"
+#include "mlp_layout.cuh"
 #include <vector>
 
 namespace cnerf {
 
 // ------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must abort the kernel, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("cnerf: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 columns of fp32: thread i <- lane (base+i), v[j] <- column (col+j)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// ------------------------------------------------------------------------------------
-// descriptors
-// ------------------------------------------------------------------------------------
-constexpr uint32_t kRows = 128;                 // tile rows (points) == N rows of one weight block
-constexpr uint32_t kLBO = kRows * 16;           // 2048 B between k-groups (8 fp16 of K)
-constexpr uint32_t kSBO = 128;                  // 8 rows x 16 B
-// K-major, SWIZZLE_NONE, version 1 (sm_100): cute::UMMA::SmemDescriptor
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
-}
-// cute::UMMA::InstrDescriptor: c=F32 (bit4), a=b=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t instr_desc(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
-
-__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// 8 fp32 -> one 16-byte hi store + one 16-byte lo store at (row, kgroup)
-__device__ __forceinline__ void store_split8(uint32_t hi_base, uint32_t lo_base, uint32_t row, uint32_t kg, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    uint32_t off = kg * kLBO + row * 16;
-    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
-    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
-}
-
-// ------------------------------------------------------------------------------------
 // The weight-block program: the order in which 16 KB blocks (128 out-rows x 32 k, hi+lo) are
 // streamed and multiplied.  Built once on the host, mirrored in constant memory.
 // ------------------------------------------------------------------------------------
-constexpr int kNumLayers = 10;                  // 0-7 pts_linears, 8 feature_linear, 9 views_linears.0
-constexpr int kMaxBlocks = 160;
-constexpr uint32_t kBlockBytes = 16384;
-constexpr uint32_t kBlockHalfBytes = 8192;
-
 struct BlkInfo {
     uint8_t layer, half, a_src, a_kg;           // a_src: 0 = encoding buffer, 1 = activation buffer
     uint8_t first, last_of_layer, wait_a, kvalid;
@@ -182,21 +63,6 @@ static std::vector<BlkInfo> build_program() {
     }
     return prog;
 }
-
-// misc fp32 parameter block
-constexpr int kMiscBias = 0;                    // [10][256]
-constexpr int kMiscAlphaW = 2560;               // [256]
-constexpr int kMiscAlphaB = 2816;               // [1]
-constexpr int kMiscRgbW = 2820;                 // [3][128]
-constexpr int kMiscRgbB = 3204;                 // [3]
-constexpr int kMiscFloats = 3208;
-
-struct RawParams {
-    const float* w[kNumLayers];
-    const float* b[kNumLayers];
-    const float* alpha_w; const float* alpha_b; const float* rgb_w; const float* rgb_b;
-    int ld[kNumLayers];
-};
 
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(RawParams p, uint8_t* __restrict__ stream) {
@@ -233,25 +99,6 @@ __global__ void pack_misc_kernel(RawParams p, float* __restrict__ misc) {
     misc[i] = v;
 }
 
-// ------------------------------------------------------------------------------------
-// shared-memory map of the fused kernel
-// ------------------------------------------------------------------------------------
-constexpr uint32_t kActHi = 0;                          // 32 k-groups x 2048 B  (K = 256)
-constexpr uint32_t kActLo = 65536;
-constexpr uint32_t kEmbHi = 131072;                     // 8 k-groups (K = 64): point encoding, later dir encoding
-constexpr uint32_t kEmbLo = 147456;
-constexpr uint32_t kRing = 163840;                      // 4 stages x 16 KB
-constexpr int kStages = 4;
-constexpr uint32_t kBars = kRing + kStages * kBlockBytes;      // 229376
-constexpr uint32_t kTmemSlot = kBars + 96;
-constexpr uint32_t kSAlpha = kBars + 128;               // float[128]
-constexpr uint32_t kSRgb = kSAlpha + 512;               // float[3][128]
-constexpr uint32_t kSmemTotal = kSRgb + 1536;           // 231552 <= 232448
-
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = kEpiThreads + 64;
-constexpr uint32_t kTmemCols = 512;
-
 // column j of the 63-wide point encoding / 27-wide direction encoding of (x0,x1,x2)
 template <int J>
 __device__ __forceinline__ float enc_col(const float (&x)[3], int width) {
@@ -284,9 +131,11 @@ __device__ __forceinline__ void write_encoding(uint32_t hi_base, uint32_t lo_bas
     }
 }
 
+template <bool kSave>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
-                 const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw) {
+                 const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
+                 uint8_t* __restrict__ acts) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,7 +180,18 @@ mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int b = 0; b < nblk; ++b, ++it) {
                     BlkInfo bi = c_blocks[b];
-                    if (bi.wait_a) { mbar_wait(bar_a, a_cnt & 1); ++a_cnt; tc_fence_after(); }
+                    if (bi.wait_a) {
+                        mbar_wait(bar_a, a_cnt & 1); ++a_cnt; tc_fence_after();
+                        if (kSave) {      // the A operand of this layer is complete in SMEM: stream it out
+                            uint8_t* rec = acts + (size_t)tile * kTileBytes;
+                            const int L = bi.layer;
+                            if (L == 0) bulk_s2g(rec + kSlotE, sbase + kEmbHi, 32768);
+                            else if (L <= 8) bulk_s2g(rec + kSlotH0 + (size_t)(L - 1) * 131072, sbase + kActHi, 131072);
+                            else bulk_s2g(rec + kSlotF, sbase + kActHi, 131072);
+                            if (L == 6) bulk_s2g(rec + kSlotV, sbase + kEmbHi, 32768);
+                            bulk_commit();
+                        }
+                    }
                     uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
@@ -348,9 +208,21 @@ mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ 
                         umma_f16(d, al, bh, idesc, 1u);
                     }
                     umma_commit(bar_empty + 8 * s);            // frees the ring slot when these MMAs retire
-                    if (bi.last_of_layer) umma_commit(bar_d);  // accumulator of the layer is complete
+                    if (bi.last_of_layer) {
+                        if (kSave) bulk_wait_read0();           // the epilogue may now overwrite the stored buffers
+                        umma_commit(bar_d);                     // accumulator of the layer is complete
+                    }
+                }
+                if (kSave) {              // views_linears output (post-ReLU) written by the last epilogue
+                    mbar_wait(bar_a, a_cnt & 1); ++a_cnt;
+                    uint8_t* rec = acts + (size_t)tile * kTileBytes;
+                    bulk_s2g(rec + kSlotHV, sbase + kActHi, 32768);
+                    bulk_s2g(rec + kSlotHV + 32768, sbase + kActLo, 32768);
+                    bulk_commit();
+                    bulk_wait_read0();    // the next tile's first epilogue overwrites the buffer only after its MMAs anyway
                 }
             }
+            if (kSave) bulk_wait0();
         }
     } else {
         // ===== prologue + epilogue warps =====
@@ -445,6 +317,11 @@ mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ 
                             r0 = fmaf(h, __ldg(misc + kMiscRgbW + c + j), r0);
                             r1 = fmaf(h, __ldg(misc + kMiscRgbW + 128 + c + j), r1);
                             r2 = fmaf(h, __ldg(misc + kMiscRgbW + 256 + c + j), r2);
+                            if (kSave) v[j] = fminf(h, 65504.f);
+                        }
+                        if (kSave) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) store_split8(sbase + kActHi, sbase + kActLo, row, (c >> 3) + g, v + 8 * g);
                         }
                     }
                     if (part == 1) { s_rgb[row] = r0; s_rgb[128 + row] = r1; s_rgb[256 + row] = r2; }
@@ -458,6 +335,7 @@ mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ 
                         *reinterpret_cast<float4*>(raw + 4 * (size_t)grow) = o;
                     }
                     // TMEM reads are ordered before the next tile's prologue arrive (tc_fence_before there)
+                    if (kSave) { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_a); }
                 }
             }
         }
@@ -535,13 +413,10 @@ umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, i
 
 using namespace cnerf;
 
-struct cnerf_weights {
-    uint8_t* stream = nullptr;     // packed fp16 hi/lo blocks in program order
-    float* misc = nullptr;         // biases + alpha/rgb heads (fp32)
-    int num_blocks = 0;
-    int device = -1;
-    bool packed = false;
-};
+namespace cnerf {
+int upload_bwd_program_once(int* nblocks);                                   // mlp_bwd_tc.cu
+int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaStream_t st);
+}
 
 static int upload_program(int* nblocks) {
     std::vector<BlkInfo> prog = build_program();
@@ -559,11 +434,13 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
     CNERF_REQUIRE(out, "cnerf_weights_create: null out");
     cnerf_weights* w = new cnerf_weights();
     int rc = upload_program(&w->num_blocks);
+    if (rc == CNERF_OK) rc = upload_bwd_program_once(&w->num_blocks_bwd);
     if (rc != CNERF_OK) { delete w; return rc; }
     cudaGetDevice(&w->device);
     cudaError_t e = cudaMalloc(&w->stream, (size_t)w->num_blocks * kBlockBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd, (size_t)w->num_blocks_bwd * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->misc, kMiscFloats * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(w->stream); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
+    if (e != cudaSuccess) { cudaFree(w->stream); cudaFree(w->stream_bwd); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
     *out = w;
     return CNERF_OK;
 }
@@ -571,6 +448,7 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
 extern "C" void cnerf_weights_destroy(cnerf_weights* w) {
     if (!w) return;
     cudaFree(w->stream);
+    cudaFree(w->stream_bwd);
     cudaFree(w->misc);
     delete w;
 }
@@ -593,31 +471,53 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     CNERF_LAUNCH_CHECK("pack_weights_kernel");
     pack_misc_kernel<<<ceil_div(kMiscFloats, 256), 256, 0, as_stream(stream)>>>(p, w->misc);
     CNERF_LAUNCH_CHECK("pack_misc_kernel");
+    int rc = pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
+    if (rc != CNERF_OK) return rc;
     w->packed = true;
     return CNERF_OK;
 }
 
-extern "C" int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                             float* raw, void* stream) {
-    CNERF_REQUIRE(w && w->packed, "cnerf_mlp_fwd: weights handle not packed (call cnerf_weights_refresh)");
-    CNERF_REQUIRE(pts && viewdirs && raw, "cnerf_mlp_fwd: null pointer");
-    CNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "cnerf_mlp_fwd: bad sizes");
+static int launch_mlp(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
+                      float* raw, void* acts, void* stream, const char* who) {
+    CNERF_REQUIRE(w && w->packed, "%s: weights handle not packed (call cnerf_weights_refresh)", who);
+    CNERF_REQUIRE(pts && viewdirs && raw, "%s: null pointer", who);
+    CNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "%s: bad sizes", who);
     int64_t np64 = (int64_t)n_rays * n_samples;
-    CNERF_REQUIRE(np64 < (int64_t)1 << 30, "cnerf_mlp_fwd: too many points in one call (%lld)", (long long)np64);
+    CNERF_REQUIRE(np64 < (int64_t)1 << 30, "%s: too many points in one call (%lld)", who, (long long)np64);
     if (np64 == 0) return CNERF_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused_kernel)");
         attr_set = true;
     }
     int n_points = (int)np64;
     int tiles = ceil_div(n_points, (int)kRows);
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    mlp_fused_kernel<<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
-                                                                      n_samples, n_rays, raw);
+    if (acts)
+        mlp_fused_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
+                                                                                n_samples, n_rays, raw, (uint8_t*)acts);
+    else
+        mlp_fused_kernel<false><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
+                                                                                 n_samples, n_rays, raw, nullptr);
     CNERF_LAUNCH_CHECK("mlp_fused_kernel");
     return CNERF_OK;
+}
+
+extern "C" int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
+                             float* raw, void* stream) {
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, stream, "cnerf_mlp_fwd");
+}
+
+extern "C" int64_t cnerf_mlp_acts_bytes(int64_t n_points) {
+    return ceil_div64(n_points, kRows) * (int64_t)kTileBytes;
+}
+
+extern "C" int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
+                                   int n_samples, float* raw, void* acts, void* stream) {
+    CNERF_REQUIRE(acts, "cnerf_mlp_fwd_train: null activation record buffer");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, acts, stream, "cnerf_mlp_fwd_train");
 }
 
 extern "C" int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream) {

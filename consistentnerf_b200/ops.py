@@ -6,6 +6,7 @@ operation runs in libcnerf.so.  All tensors must be CUDA float32.
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import List, Optional, Sequence, Tuple
 
@@ -366,12 +367,45 @@ def fused_mlp_forward(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.
     return raw
 
 
-BWD_CHUNK_POINTS = 1 << 18      # activation recompute granularity of the backward pass
+BWD_CHUNK_POINTS = 1 << 18      # activation recompute granularity of the CUDA-core backward pass
+MLP_BWD = os.environ.get("CNERF_MLP_BWD", "tc")      # "tc": tcgen05 backward, "simt": fp32 CUDA-core backward
+
+
+def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor):
+    """Training-mode forward: raw [n,S,4] plus the activation record the tensor-core backward reads."""
+    n, S = pts.shape[0], pts.shape[1]
+    raw = torch.empty((n, S, 4), device=pts.device, dtype=_F32)
+    nbytes = int(_lib.load().cnerf_mlp_acts_bytes(n * S))
+    acts = torch.empty(nbytes, device=pts.device, dtype=torch.uint8)
+    call("cnerf_mlp_fwd_train", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ptr(acts), stream())
+    return raw, acts
+
+
+def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw: torch.Tensor, n_points: int,
+                       return_record: bool = False):
+    """Parameter gradients of the canonical network from d_raw [n_points,4] and the forward's activation record."""
+    dev = acts.device
+    d_raw = _f32c(d_raw).reshape(n_points, 4)
+    grads = {k: torch.empty_like(v) for k, v in P.items()}
+    lib = _lib.load()
+    rec = torch.empty(int(lib.cnerf_mlp_grads_bytes(n_points)), device=dev, dtype=torch.uint8)
+    ws = _workspace(dev, int(lib.cnerf_mlp_bwd_workspace_bytes()))
+    pw = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.weight"].data_ptr() for i in range(8)])
+    pb = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.bias"].data_ptr() for i in range(8)])
+    call("cnerf_mlp_bwd", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, pw, pb,
+         ptr(grads["feature_linear.weight"]), ptr(grads["feature_linear.bias"]),
+         ptr(grads["alpha_linear.weight"]), ptr(grads["alpha_linear.bias"]),
+         ptr(grads["views_linears.0.weight"]), ptr(grads["views_linears.0.bias"]),
+         ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), 0, ptr(ws), stream())
+    if return_record:
+        return grads, rec
+    return grads
 
 
 class FusedMLPFn(torch.autograd.Function):
-    """run_network (embed + NeRF) with the tcgen05 forward.  Backward recomputes the activations
-    chunk by chunk with the fp32 layer kernels and accumulates the parameter gradients."""
+    """run_network (embed + NeRF) on tcgen05.  Training: the forward also streams the activation record, the
+    backward (data-gradient chain + weight-gradient GEMMs, same fp16x3 split) runs on the tensor cores too.
+    CNERF_MLP_BWD=simt selects the fp32 CUDA-core backward (activation recompute, any architecture)."""
 
     @staticmethod
     def forward(ctx, spec: MLPSpec, packed: PackedWeights, multires: int, multires_views: int, pts, viewdirs, *params):
@@ -379,14 +413,29 @@ class FusedMLPFn(torch.autograd.Function):
         P = {n: p.detach() for n, p in zip(names, params)}
         packed.refresh(P)
         pts_c, vd_c = _f32c(pts.detach()), _f32c(viewdirs.detach())
-        raw = fused_mlp_forward(packed, pts_c, vd_c)
-        ctx.spec, ctx.P, ctx.enc = spec, P, (multires, multires_views)
-        ctx.save_for_backward(pts_c, vd_c)
+        ctx.spec, ctx.P, ctx.enc, ctx.packed = spec, P, (multires, multires_views), packed
+        ctx.tc = MLP_BWD == "tc" and any(ctx.needs_input_grad[6:])
+        if ctx.tc:
+            raw, acts = fused_mlp_forward_train(packed, pts_c, vd_c)
+            ctx.pack_key = packed._key
+            ctx.save_for_backward(acts)
+            ctx.n_points = pts_c.shape[0] * pts_c.shape[1]
+        else:
+            raw = fused_mlp_forward(packed, pts_c, vd_c)
+            ctx.save_for_backward(pts_c, vd_c)
         return raw
 
     @staticmethod
     def backward(ctx, d_raw):
         spec, P = ctx.spec, ctx.P
+        names = spec.param_names()
+        if ctx.tc:
+            (acts,) = ctx.saved_tensors
+            packed = ctx.packed
+            if packed._key != ctx.pack_key:
+                raise RuntimeError("parameters were modified in place between the forward and the backward pass")
+            grads = fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points)
+            return (None, None, None, None, None, None) + tuple(grads[k] for k in names)
         L, Lv = ctx.enc
         pts, viewdirs = ctx.saved_tensors
         n, S = pts.shape[0], pts.shape[1]
@@ -403,7 +452,7 @@ class FusedMLPFn(torch.autograd.Function):
             _, saved = _layerwise_forward(spec, P, x)
             _layerwise_backward(spec, P, saved, d_raw[r0 * S:r1 * S], grads, False, not first)
             first = False
-        return (None, None, None, None, None, None) + tuple(grads[k] for k in spec.param_names())
+        return (None, None, None, None, None, None) + tuple(grads[k] for k in names)
 
 
 # ----------------------------------------------------------------------------------------

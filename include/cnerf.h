@@ -118,6 +118,23 @@ int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w, const flo
 /* raw[n_rays*n_samples, 4] = NeRF(embed(pts), embed(viewdirs[ray])). */
 int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
                   int n_samples, float* raw, void* stream);
+/* Training-mode forward: same result as cnerf_mlp_fwd, and every layer's A operand (encodings, post-activation
+ * outputs; fp16 hi/lo tiles) is streamed into `acts` (cnerf_mlp_acts_bytes(n_rays*n_samples) bytes, device) for
+ * cnerf_mlp_bwd. */
+int64_t cnerf_mlp_acts_bytes(int64_t n_points);
+int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
+                        float* raw, void* acts, void* stream);
+/* K3b backward on tensor cores (autograd of run_network w.r.t. the parameters; loss.backward() of
+ * NP/run_nerf_view.py:1982 for this module).  d_raw [n_points,4]; `acts` from cnerf_mlp_fwd_train with the SAME packed
+ * weights; `grads_rec` scratch of cnerf_mlp_grads_bytes(n_points) bytes; `workspace` of
+ * cnerf_mlp_bwd_workspace_bytes() bytes.  Outputs are the gradients of the twelve nn.Linear layers in their
+ * [out,in] / [out] shapes (overwritten, or added to when accumulate != 0).  Deterministic. */
+int64_t cnerf_mlp_grads_bytes(int64_t n_points);
+int64_t cnerf_mlp_bwd_workspace_bytes(void);
+int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
+                  float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
+                  float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
+                  float* d_rgb_b, int accumulate, void* workspace, void* stream);
 /* Unit self-test of the tcgen05 building blocks: d[128,n] = a[128,k] b[n,k]^T with the same
  * fp16 hi/lo split, descriptors and TMEM read-back the fused kernel uses (k%16==0, n%16==0, n<=256). */
 int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream);

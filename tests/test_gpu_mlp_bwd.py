@@ -1,0 +1,141 @@
+"""Stage-wise parity of the tensor-core MLP backward (K3b): activation record of the training forward, the
+data-gradient chain's G tiles, and the parameter gradients, each against an fp64 restatement
+(NP/run_nerf_helpers.py:107-130 differentiated by torch autograd)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from util import ARCH, module_from_params, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TILE = 1310720
+SLOT_E, SLOT_H0, SLOT_F, SLOT_V, SLOT_HV = 0, 32768, 32768 + 8 * 131072, 32768 + 9 * 131072, 32768 + 9 * 131072 + 32768
+GTILE = 65536 + 9 * 131072
+
+
+def g_slot(l):
+    return 0 if l == 9 else 65536 + (8 - l) * 131072
+
+
+def decode(rec_u8, tile_bytes, slot, kgroups, lo_off, n_points):
+    """[n_points, 8*kgroups] float64 = hi + lo from the fp16 UMMA tiles of every 128-point record."""
+    rec = rec_u8.cpu().numpy().reshape(-1, tile_bytes)
+    out = []
+    for t in range(rec.shape[0]):
+        hi = rec[t, slot:slot + kgroups * 2048].view(np.float16).reshape(kgroups, 128, 8)
+        lo = rec[t, slot + lo_off:slot + lo_off + kgroups * 2048].view(np.float16).reshape(kgroups, 128, 8)
+        v = hi.astype(np.float64) + lo.astype(np.float64)
+        out.append(v.transpose(1, 0, 2).reshape(128, kgroups * 8))
+    return torch.from_numpy(np.concatenate(out, 0)[:n_points])
+
+
+def reference_chain(p, pts, vd, d_raw):
+    """fp64 forward keeping every pre-activation as a leaf-like tensor with retained gradient."""
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    n, S = pts.shape[:2]
+    e = O.posenc(pts.double().reshape(-1, 3), 10)
+    ev = O.posenc(vd.double()[:, None, :].expand(n, S, 3).reshape(-1, 3), 4)
+    pre, post = [], []
+    h = e
+    for i in range(8):
+        z = h @ p64[f"pts_linears.{i}.weight"].t() + p64[f"pts_linears.{i}.bias"]
+        z.retain_grad(); pre.append(z)
+        h = torch.relu(z); post.append(h)
+        if i == 4:
+            h = torch.cat([e, h], -1)
+    sigma = h @ p64["alpha_linear.weight"].t() + p64["alpha_linear.bias"]
+    feat = h @ p64["feature_linear.weight"].t() + p64["feature_linear.bias"]
+    feat.retain_grad()
+    zv = torch.cat([feat, ev], -1) @ p64["views_linears.0.weight"].t() + p64["views_linears.0.bias"]
+    zv.retain_grad()
+    hv = torch.relu(zv)
+    rgb = hv @ p64["rgb_linear.weight"].t() + p64["rgb_linear.bias"]
+    raw = torch.cat([rgb, sigma], -1)
+    raw.backward(d_raw.double())
+    return dict(p64=p64, e=e, ev=ev, pre=pre, post=post, feat=feat, zv=zv, hv=hv, raw=raw)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import consistentnerf_b200 as cn
+    p = O.make_params(17, sigma_bias=0.3, **ARCH)
+    net = module_from_params(p, ARCH)
+    gen = torch.Generator().manual_seed(3)
+    n, S = 5, 60                                   # 300 points: two full tiles + a ragged one
+    pts = torch.randn(n, S, 3, generator=gen) * 1.5
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    d_raw = torch.randn(n * S, 4, generator=gen) * 1e-6      # realistic tiny loss gradients
+    packed = net.packed_weights()
+    P = {k: v.detach() for k, v in zip(net.spec.param_names(), net.hot_params())}
+    packed.refresh(P)
+    raw, acts = cn.ops.fused_mlp_forward_train(packed, pts.to(DEV), vd.to(DEV))
+    ref = reference_chain(p, pts, vd, d_raw)
+    return dict(cn=cn, p=p, net=net, packed=packed, P=P, pts=pts, vd=vd, d_raw=d_raw, raw=raw, acts=acts, ref=ref, n=n * S)
+
+
+def test_training_forward_equals_inference_forward(setup):
+    cn = setup["cn"]
+    raw2 = cn.ops.fused_mlp_forward(setup["packed"], setup["pts"].to(DEV), setup["vd"].to(DEV))
+    assert torch.equal(raw2, setup["raw"])
+    assert rel_err(setup["raw"].reshape(-1, 4), setup["ref"]["raw"]) < 2e-5
+
+
+def test_activation_record(setup):
+    acts, ref, n = setup["acts"], setup["ref"], setup["n"]
+    assert acts.numel() == 3 * TILE
+    E = decode(acts, TILE, SLOT_E, 8, 16384, n)
+    assert rel_err(E[:, :63], ref["e"]) < 2e-6 and float(E[:, 63].abs().max()) == 0.0
+    for l in range(8):
+        H = decode(acts, TILE, SLOT_H0 + l * 131072, 32, 65536, n)
+        assert rel_err(H, ref["post"][l]) < 5e-6, l
+    F = decode(acts, TILE, SLOT_F, 32, 65536, n)
+    assert rel_err(F, ref["feat"]) < 5e-6
+    V = decode(acts, TILE, SLOT_V, 4, 16384, n)
+    assert rel_err(V[:, :27], ref["ev"]) < 2e-6
+    HV = decode(acts, TILE, SLOT_HV, 16, 32768, n)
+    assert rel_err(HV, ref["hv"]) < 5e-6
+
+
+def test_gradient_chain_and_parameter_gradients(setup):
+    cn, ref, n = setup["cn"], setup["ref"], setup["n"]
+    grads, rec = cn.ops.fused_mlp_backward(setup["packed"], setup["P"], setup["acts"], setup["d_raw"].to(DEV), n,
+                                           return_record=True)
+    torch.cuda.synchronize()
+    amax = float(setup["d_raw"].abs().max())
+    scale = 2.0 ** math.floor(math.log2(256.0 / amax))
+    errs = {}
+    G9 = decode(rec, GTILE, g_slot(9), 16, 32768, n) / scale
+    errs["G9"] = rel_err(G9, ref["zv"].grad)
+    G8 = decode(rec, GTILE, g_slot(8), 32, 65536, n) / scale
+    errs["G8"] = rel_err(G8, ref["feat"].grad)
+    for l in range(7, -1, -1):
+        G = decode(rec, GTILE, g_slot(l), 32, 65536, n) / scale
+        errs[f"G{l}"] = rel_err(G, ref["pre"][l].grad)
+    print("chain:", {k: f"{v:.1e}" for k, v in errs.items()})
+    perr = {k: rel_err(grads[k], ref["p64"][k].grad) for k in grads}
+    print("params:", {k: f"{v:.1e}" for k, v in perr.items()})
+    assert all(v < 2e-5 for v in errs.values()), errs
+    assert all(v < 2e-5 for v in perr.values()), perr
+
+
+def test_autograd_path_matches_cuda_core_backward(setup):
+    """render-level: the tensor-core backward and the fp32 CUDA-core backward give the same parameter gradients."""
+    cn, net = setup["cn"], setup["net"]
+    e, _ = cn.get_embedder(10)
+    ev, _ = cn.get_embedder(4)
+    pts, vd = setup["pts"].to(DEV), setup["vd"].to(DEV)
+    g = torch.randn(5, 60, 4, generator=torch.Generator().manual_seed(9)).to(DEV) * 1e-5
+    out = {}
+    for mode in ("tc", "simt"):
+        cn.ops.MLP_BWD = mode
+        net.zero_grad()
+        cn.run_network(pts, vd, net, e, ev).backward(g)
+        out[mode] = {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None}
+    cn.ops.MLP_BWD = "tc"
+    for k in out["tc"]:
+        assert rel_err(out["tc"][k], out["simt"][k]) < 2e-5, k
