@@ -601,17 +601,11 @@ int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaSt
 extern "C" int64_t cnerf_mlp_grads_bytes(int64_t n_points) { return ceil_div64(n_points, kRows) * (int64_t)kGTileBytes; }
 extern "C" int64_t cnerf_mlp_bwd_workspace_bytes(void) { return (int64_t)kWsBytes; }
 
-extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
-                             float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
-                             float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
-                             float* d_rgb_b, int accumulate, void* workspace, void* stream) {
-    CNERF_REQUIRE(w && w->packed && w->stream_bwd, "cnerf_mlp_bwd: weights handle not packed");
-    CNERF_REQUIRE(d_raw && acts && grads_rec && workspace && d_pts_w && d_pts_b && d_feature_w && d_feature_b && d_alpha_w &&
-                      d_alpha_b && d_views_w && d_views_b && d_rgb_w && d_rgb_b, "cnerf_mlp_bwd: null pointer");
-    CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd: negative n_points");
-    for (int i = 0; i < 8; ++i) CNERF_REQUIRE(d_pts_w[i] && d_pts_b[i], "cnerf_mlp_bwd: null pts_linears.%d gradient", i);
-    if (n_points == 0) return CNERF_OK;
-    cudaStream_t st = as_stream(stream);
+namespace {
+struct BwdCtx {
+    cudaStream_t st; uint32_t* amax; float *dw_part, *db_part, *head_part; const uint8_t* a; uint8_t* g; int tiles, grid;
+};
+int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, void* stream, BwdCtx* c) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -620,42 +614,80 @@ extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const v
         attr_set = true;
     }
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-    uint32_t* amax = reinterpret_cast<uint32_t*>(ws + kWsAmax);
-    float* dw_part = reinterpret_cast<float*>(ws + kWsDwPart);
-    float* db_part = reinterpret_cast<float*>(ws + kWsDbPart);
-    float* head_part = reinterpret_cast<float*>(ws + kWsHeadPart);
-    const uint8_t* a = reinterpret_cast<const uint8_t*>(acts);
-    uint8_t* g = reinterpret_cast<uint8_t*>(grads_rec);
-    const int tiles = ceil_div(n_points, (int)kRows);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    c->st = as_stream(stream);
+    c->amax = reinterpret_cast<uint32_t*>(ws + kWsAmax);
+    c->dw_part = reinterpret_cast<float*>(ws + kWsDwPart);
+    c->db_part = reinterpret_cast<float*>(ws + kWsDbPart);
+    c->head_part = reinterpret_cast<float*>(ws + kWsHeadPart);
+    c->a = reinterpret_cast<const uint8_t*>(acts);
+    c->g = reinterpret_cast<uint8_t*>(grads_rec);
+    c->tiles = ceil_div(n_points, (int)kRows);
+    c->grid = c->tiles < kNumSMs ? c->tiles : kNumSMs;
+    return CNERF_OK;
+}
+}  // namespace
 
-    cudaError_t e = cudaMemsetAsync(amax, 0, 4, st);
+// Stage 1: gradient scale + data-gradient chain -> grads_rec (G tiles of every layer).
+extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec,
+                                  int n_points, void* workspace, void* stream) {
+    CNERF_REQUIRE(w && w->packed && w->stream_bwd, "cnerf_mlp_bwd_data: weights handle not packed");
+    CNERF_REQUIRE(d_raw && acts && grads_rec && workspace, "cnerf_mlp_bwd_data: null pointer");
+    CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_data: negative n_points");
+    if (n_points == 0) return CNERF_OK;
+    BwdCtx c;
+    int rc = bwd_ctx(acts, grads_rec, n_points, workspace, stream, &c);
+    if (rc != CNERF_OK) return rc;
+    cudaError_t e = cudaMemsetAsync(c.amax, 0, 4, c.st);
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
-    absmax_kernel<<<kNumSMs, 256, 0, st>>>(d_raw, (int64_t)n_points * 4, amax);
+    absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
-
-    mlp_bwd_data_kernel<<<grid, kThreads, kSmemTotal, st>>>(w->stream_bwd, w->misc, d_raw, a, amax, n_points, g);
+    mlp_bwd_data_kernel<<<c.grid, kThreads, kSmemTotal, c.st>>>(w->stream_bwd, w->misc, d_raw, c.a, c.amax, n_points, c.g);
     CNERF_LAUNCH_CHECK("mlp_bwd_data_kernel");
+    return CNERF_OK;
+}
 
-    mlp_heads_grad_kernel<<<grid, 256, 0, st>>>(d_raw, a, n_points, head_part);
+// Stage 3: the two narrow heads (needs only d_raw and the activation record).
+extern "C" int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, float* d_alpha_w, float* d_alpha_b,
+                                   float* d_rgb_w, float* d_rgb_b, int accumulate, void* workspace, void* stream) {
+    CNERF_REQUIRE(d_raw && acts && workspace && d_alpha_w && d_alpha_b && d_rgb_w && d_rgb_b, "cnerf_mlp_bwd_heads: null pointer");
+    CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_heads: negative n_points");
+    if (n_points == 0) return CNERF_OK;
+    BwdCtx c;
+    int rc = bwd_ctx(acts, nullptr, n_points, workspace, stream, &c);
+    if (rc != CNERF_OK) return rc;
+    mlp_heads_grad_kernel<<<c.grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
     CNERF_LAUNCH_CHECK("mlp_heads_grad_kernel");
-    heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, st>>>(head_part, grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
+    heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, c.st>>>(c.head_part, c.grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
     CNERF_LAUNCH_CHECK("heads_reduce_kernel");
+    return CNERF_OK;
+}
 
-    // weight-gradient passes
+// Stage 2: weight / bias gradients of the ten GEMM layers from grads_rec (after cnerf_mlp_bwd_data on the same workspace).
+extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, int n_points, float* const* d_pts_w,
+                                     float* const* d_pts_b, float* d_feature_w, float* d_feature_b, float* d_views_w,
+                                     float* d_views_b, int accumulate, void* workspace, void* stream) {
+    CNERF_REQUIRE(acts && grads_rec && workspace && d_pts_w && d_pts_b && d_feature_w && d_feature_b && d_views_w && d_views_b,
+                  "cnerf_mlp_bwd_weights: null pointer");
+    CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_weights: negative n_points");
+    for (int i = 0; i < 8; ++i) CNERF_REQUIRE(d_pts_w[i] && d_pts_b[i], "cnerf_mlp_bwd_weights: null pts_linears.%d gradient", i);
+    if (n_points == 0) return CNERF_OK;
+    BwdCtx c;
+    int rc = bwd_ctx(acts, const_cast<void*>(grads_rec), n_points, workspace, stream, &c);
+    if (rc != CNERF_OK) return rc;
+    cudaStream_t st = c.st;
+    const int grid = c.grid, tiles = c.tiles;
     auto H = [](int l) { return (uint32_t)(kSlotH0 + (size_t)l * 131072); };
     auto run_pass = [&](const DwPass& P, const DwSegs& S, float* db0, int n0, float* db1, int n1) -> int {
-        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(P, a, g, tiles, dw_part, db_part);
+        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(P, c.a, c.g, tiles, c.dw_part, c.db_part);
         CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
         int maxc = 0;
         for (int i = 0; i < S.n; ++i) maxc = S.s[i].ncols > maxc ? S.s[i].ncols : maxc;
-        dw_reduce_kernel<<<dim3(ceil_div(128 * maxc, 256), S.n), 256, 0, st>>>(S, dw_part, grid, amax, accumulate);
+        dw_reduce_kernel<<<dim3(ceil_div(128 * maxc, 256), S.n), 256, 0, st>>>(S, c.dw_part, grid, c.amax, accumulate);
         CNERF_LAUNCH_CHECK("dw_reduce_kernel");
-        if (db0) { db_reduce_kernel<<<ceil_div(n0, 256), 256, 0, st>>>(db0, n0, db_part, 0, grid, amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
-        if (db1) { db_reduce_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(db1, n1, db_part, 1, grid, amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
+        if (db0) { db_reduce_kernel<<<ceil_div(n0, 256), 256, 0, st>>>(db0, n0, c.db_part, 0, grid, c.amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
+        if (db1) { db_reduce_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(db1, n1, c.db_part, 1, grid, c.amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
         return CNERF_OK;
     };
-    int rc;
     {   // encoding pass: dW0 = G0^T E, dW5[:, :63] = G5^T E
         DwPass P = {}; P.n_a = 2; P.n_x = 1; P.db_mask = 3;
         P.a[0] = {(uint32_t)g_slot(0), 32, 65536}; P.a[1] = {(uint32_t)g_slot(5), 32, 65536}; P.x[0] = {(uint32_t)kSlotE, 8, 16384};
@@ -686,4 +718,15 @@ extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const v
         if ((rc = run_pass(P, S, d_views_b, 128, nullptr, 0)) != CNERF_OK) return rc;
     }
     return CNERF_OK;
+}
+
+extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
+                             float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
+                             float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
+                             float* d_rgb_b, int accumulate, void* workspace, void* stream) {
+    int rc = cnerf_mlp_bwd_data(w, d_raw, acts, grads_rec, n_points, workspace, stream);
+    if (rc == CNERF_OK) rc = cnerf_mlp_bwd_heads(d_raw, acts, n_points, d_alpha_w, d_alpha_b, d_rgb_w, d_rgb_b, accumulate, workspace, stream);
+    if (rc == CNERF_OK) rc = cnerf_mlp_bwd_weights(acts, grads_rec, n_points, d_pts_w, d_pts_b, d_feature_w, d_feature_b, d_views_w,
+                                                   d_views_b, accumulate, workspace, stream);
+    return rc;
 }

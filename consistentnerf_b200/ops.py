@@ -392,11 +392,13 @@ def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw
     ws = _workspace(dev, int(lib.cnerf_mlp_bwd_workspace_bytes()))
     pw = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.weight"].data_ptr() for i in range(8)])
     pb = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.bias"].data_ptr() for i in range(8)])
-    call("cnerf_mlp_bwd", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, pw, pb,
-         ptr(grads["feature_linear.weight"]), ptr(grads["feature_linear.bias"]),
-         ptr(grads["alpha_linear.weight"]), ptr(grads["alpha_linear.bias"]),
-         ptr(grads["views_linears.0.weight"]), ptr(grads["views_linears.0.bias"]),
-         ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), 0, ptr(ws), stream())
+    st = stream()
+    call("cnerf_mlp_bwd_data", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, ptr(ws), st)
+    call("cnerf_mlp_bwd_heads", ptr(d_raw), ptr(acts), n_points, ptr(grads["alpha_linear.weight"]),
+         ptr(grads["alpha_linear.bias"]), ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), 0, ptr(ws), st)
+    call("cnerf_mlp_bwd_weights", ptr(acts), ptr(rec), n_points, pw, pb, ptr(grads["feature_linear.weight"]),
+         ptr(grads["feature_linear.bias"]), ptr(grads["views_linears.0.weight"]), ptr(grads["views_linears.0.bias"]),
+         0, ptr(ws), st)
     if return_record:
         return grads, rec
     return grads

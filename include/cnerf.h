@@ -135,6 +135,15 @@ int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, 
                   float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
                   float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
                   float* d_rgb_b, int accumulate, void* workspace, void* stream);
+/* The three stages of cnerf_mlp_bwd as separate calls (same buffers and workspace; cnerf_mlp_bwd_data first):
+ * the data-gradient chain, the weight/bias gradients of the ten GEMM layers, the two narrow heads. */
+int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
+                       void* workspace, void* stream);
+int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, int n_points, float* const* d_pts_w,
+                          float* const* d_pts_b, float* d_feature_w, float* d_feature_b, float* d_views_w,
+                          float* d_views_b, int accumulate, void* workspace, void* stream);
+int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, float* d_alpha_w, float* d_alpha_b,
+                        float* d_rgb_w, float* d_rgb_b, int accumulate, void* workspace, void* stream);
 /* Unit self-test of the tcgen05 building blocks: d[128,n] = a[128,k] b[n,k]^T with the same
  * fp16 hi/lo split, descriptors and TMEM read-back the fused kernel uses (k%16==0, n%16==0, n<=256). */
 int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream);

@@ -238,7 +238,10 @@ def test_sample_pdf_det_linspace_and_module_api(cn):
     bins, w = t(g["bins"], device=DEV), t(g["weights"], device=DEV)
     s = cn.sample_pdf(bins, w, 128, det=True)
     assert torch.equal(s.cpu(), t(g["samples_det"]))
-    assert torch.equal(cn.sample_pdf(bins, w, 128, det=True, pytest=True).cpu(), t(g["samples_det"]))
+    # pytest hook + det: the reference takes u from np.linspace (float64 -> float32), NP/run_nerf_helpers.py:222-225
+    u_np = torch.tensor(np.broadcast_to(np.linspace(0.0, 1.0, 128), (48, 128)).copy(), dtype=torch.float32)
+    assert torch.equal(cn.sample_pdf(bins, w, 128, det=True, pytest=True).cpu(),
+                       O.sample_pdf(t(g["bins"]), t(g["weights"]), u_np))
 
 
 def test_sample_pdf_degenerate_weights(cn):
