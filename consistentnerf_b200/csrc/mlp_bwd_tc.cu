@@ -18,6 +18,7 @@
 // Gradients are tiny (mean losses over thousands of rays), so G is carried times a power-of-two scale derived
 // on the device from max|d_raw| (no host sync); the final reductions multiply by its exact inverse.
 #include "mlp_layout.cuh"
+#include <cuda.h>
 #include <vector>
 
 namespace cnerf {
@@ -275,6 +276,9 @@ mlp_bwd_data_kernel(const uint8_t* __restrict__ wstream, const float* __restrict
 // 2. weight gradients: D[n_out, k_in] = sum_p G[p, n_out] X[p, k_in]
 // ------------------------------------------------------------------------------------
 struct DwSrc { uint32_t slot_off, kgroups, lo_off; };        // hi k-groups at slot_off, lo k-groups at slot_off + lo_off
+// The records are 2-D arrays of 2048-byte k-group rows (128 points x 16 B); a stage takes the 512-byte column
+// window of one 32-point quarter from all k-group rows of a source with ONE TMA tensor copy (box = rows x 512 B)
+// -- 128 separate 512-byte bulk copies per stage were TMA-issue bound (ncu: 8.4k cycles per stage).
 struct DwPass {
     int n_a, n_x;
     DwSrc a[2];            // G sources in the gradient record (kgroups 32 -> two 128-row halves, 16 -> one)
@@ -289,8 +293,14 @@ constexpr uint32_t kDwSmem = kDwBars + 128;
 constexpr int kDwThreads = 320;                               // 8 reduction/epilogue warps, loader warp, MMA warp
 constexpr uint32_t kQuarter = 512;                            // bytes of one k-group for 32 points
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t x, uint32_t y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(kDwThreads, 1)
-mlp_bwd_weight_kernel(DwPass P, const uint8_t* __restrict__ acts, const uint8_t* __restrict__ grads, int num_tiles,
+mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x0,
+                      const __grid_constant__ CUtensorMap map_x1, DwPass P, int num_tiles,
                       float* __restrict__ dw_part, float* __restrict__ db_part) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -321,24 +331,23 @@ mlp_bwd_weight_kernel(DwPass P, const uint8_t* __restrict__ acts, const uint8_t*
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 8) {
-        // ===== loader: per (tile, quarter) one stage; every k-group quarter is a 512-byte bulk copy =====
-        for (int it = 0; it < n_stage_iters; ++it) {
-            const int tile = t0 + (it >> 2), q = it & 3;
-            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
-            if (lane == 0) {
+        // ===== loader: per (tile, quarter) one stage; one TMA box copy per source (two when hi / lo rows are apart) =====
+        if (lane == 0) {
+            for (int it = 0; it < n_stage_iters; ++it) {
+                const int tile = t0 + (it >> 2), q = it & 3;
+                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
-            }
-            __syncwarp();
-            const uint32_t dst0 = sbase + s * kDwStageBytes;
-            for (int i = 0; i < P.n_a + P.n_x; ++i) {
-                const bool is_a = i < P.n_a;
-                const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
-                const uint8_t* g = (is_a ? grads + (size_t)tile * kGTileBytes : acts + (size_t)tile * kTileBytes) + src.slot_off + q * kQuarter;
-                const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
-                for (uint32_t c = lane; c < 2 * src.kgroups; c += 32) {    // c < kgroups: hi k-group c, else lo k-group c - kgroups
-                    const size_t so = c < src.kgroups ? (size_t)c * 2048 : (size_t)src.lo_off + (size_t)(c - src.kgroups) * 2048;
-                    bulk_g2s(d + c * kQuarter, g + so, kQuarter, bar_full + 8 * s);
+                const uint32_t dst0 = sbase + s * kDwStageBytes;
+                for (int i = 0; i < P.n_a + P.n_x; ++i) {
+                    const bool is_a = i < P.n_a;
+                    const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
+                    const CUtensorMap* map = is_a ? &map_a : (i - P.n_a == 0 ? &map_x0 : &map_x1);
+                    const uint32_t row0 = (uint32_t)tile * (uint32_t)((is_a ? kGTileBytes : kTileBytes) / 2048) + src.slot_off / 2048;
+                    const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
+                    tma_load_2d(d, map, q * 256, row0, bar_full + 8 * s);                 // box rows = 2*kgroups or kgroups
+                    if (src.lo_off != src.kgroups * 2048)
+                        tma_load_2d(d + src.kgroups * kQuarter, map, q * 256, row0 + src.lo_off / 2048, bar_full + 8 * s);
                 }
             }
         }
@@ -602,6 +611,33 @@ extern "C" int64_t cnerf_mlp_grads_bytes(int64_t n_points) { return ceil_div64(n
 extern "C" int64_t cnerf_mlp_bwd_workspace_bytes(void) { return (int64_t)kWsBytes; }
 
 namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// record buffer as [rows][1024 x u16] (2048-byte k-group rows); box = box_rows x 256 u16 (one 32-point quarter)
+int make_record_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {1024, rows};
+    cuuint64_t gstride[1] = {2048};
+    cuuint32_t box[2] = {256, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CNERF_OK;
+}
 struct BwdCtx {
     cudaStream_t st; uint32_t* amax; float *dw_part, *db_part, *head_part; const uint8_t* a; uint8_t* g; int tiles, grid;
 };
@@ -677,8 +713,15 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
     cudaStream_t st = c.st;
     const int grid = c.grid, tiles = c.tiles;
     auto H = [](int l) { return (uint32_t)(kSlotH0 + (size_t)l * 131072); };
+    const uint64_t a_rows = (uint64_t)tiles * (kTileBytes / 2048), g_rows = (uint64_t)tiles * (kGTileBytes / 2048);
+    auto box_rows = [](const DwSrc& s) { return s.lo_off == s.kgroups * 2048 ? 2 * s.kgroups : s.kgroups; };
     auto run_pass = [&](const DwPass& P, const DwSegs& S, float* db0, int n0, float* db1, int n1) -> int {
-        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(P, c.a, c.g, tiles, c.dw_part, c.db_part);
+        CUtensorMap ma, mx0, mx1;
+        int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]));
+        if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]));
+        if (r == CNERF_OK) r = make_record_map(&mx1, c.a, a_rows, box_rows(P.x[P.n_x - 1]));
+        if (r != CNERF_OK) return r;
+        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(ma, mx0, mx1, P, tiles, c.dw_part, c.db_part);
         CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
         int maxc = 0;
         for (int i = 0; i < S.n; ++i) maxc = S.s[i].ncols > maxc ? S.s[i].ncols : maxc;
