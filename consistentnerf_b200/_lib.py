@@ -44,7 +44,10 @@ SIGNATURES = {
     "cnerf_mlp_bwd_data": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "cnerf_mlp_bwd_weights": (_I, [_P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _I, _P, _P]),
     "cnerf_mlp_bwd_heads": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
+    "cnerf_debug_profile": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cnerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_sample_pdf": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -49,8 +49,13 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     Canonical network + reference encoders: one fused tcgen05 kernel (encoding never touches HBM,
     ``netchunk`` is irrelevant).  Anything else: encoding kernel + generic layer kernels."""
     if _fusable(fn, embed_fn, embeddirs_fn, inputs, viewdirs):
+        params = fn.hot_params()
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):      # inference: nothing to record
+            packed = fn.packed_weights()
+            packed.refresh(dict(zip(fn.spec.param_names(), params)))
+            return ops.fused_mlp_forward(packed, inputs.detach(), viewdirs.detach())
         return ops.FusedMLPFn.apply(fn.spec, fn.packed_weights(), embed_fn.num_freqs, embeddirs_fn.num_freqs,
-                                    inputs, viewdirs, *fn.hot_params())
+                                    inputs, viewdirs, *params)
     inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(inputs_flat)
     if viewdirs is not None:

@@ -147,6 +147,8 @@ int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, floa
 /* Unit self-test of the tcgen05 building blocks: d[128,n] = a[128,k] b[n,k]^T with the same
  * fp16 hi/lo split, descriptors and TMEM read-back the fused kernel uses (k%16==0, n%16==0, n<=256). */
 int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream);
+/* Same product with the A operand staged in tensor memory (tcgen05.st + TS-mode MMA); k <= 256. */
+int cnerf_umma_selftest_ts(const float* a, const float* b, int n, int k, float* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 alpha compositing -- raw2outputs NP/run_nerf.py:265-308 (depth_map as returned by
@@ -218,6 +220,12 @@ int cnerf_masked_mse_fwd(const float* pred, const float* target, const float* ma
 int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* mask, int n, int C,
                          float divisor, float coef, float n_ref, int use_unmasked, const float* out,
                          const float* g_loss, float* d_pred, void* stream);
+
+/* Debug aid: enable/disable the in-kernel phase profile of the fused MLP kernel and read + clear its 16 cycle
+ * counters (host pointer, may be NULL).  Synchronises the device. */
+int cnerf_debug_profile(int enable, unsigned long long* out16);
+/* Debug aid: measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */
+int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream);
 
 #ifdef __cplusplus
 }

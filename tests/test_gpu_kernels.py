@@ -126,6 +126,15 @@ def test_umma_building_blocks(cn, n, k):
     assert rel_err(d, ref) < 2e-6
 
 
+@pytest.mark.parametrize("n,k", [(128, 64), (256, 128), (16, 16), (48, 128), (128, 256)])
+def test_umma_a_operand_in_tensor_memory(cn, n, k):
+    gen = torch.Generator().manual_seed(n * 1000 + k + 1)
+    a = torch.randn(128, k, generator=gen)
+    b = torch.randn(n, k, generator=gen) * 0.1
+    d = cn.ops.umma_selftest(a.to(DEV), b.to(DEV), a_in_tmem=True)
+    assert rel_err(d, a.double() @ b.double().t()) < 2e-6
+
+
 @pytest.mark.parametrize("n_rays,n_samples", [(1, 1), (3, 64), (40, 192), (257, 33)])
 def test_fused_mlp_forward(cn, n_rays, n_samples):
     p = O.make_params(7, sigma_bias=0.3, **ARCH)
