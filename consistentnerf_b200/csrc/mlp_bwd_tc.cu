@@ -19,6 +19,7 @@
 // on the device from max|d_raw| (no host sync); the final reductions multiply by its exact inverse.
 #include "mlp_layout.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace cnerf {
@@ -270,6 +271,232 @@ mlp_bwd_data_kernel(const uint8_t* __restrict__ wstream, const float* __restrict
     tc_fence_before();
     __syncthreads();
     if (warp == 9) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------
+// 1b. data-gradient chain, N=256 / double-buffered accumulator / k-block pipelined (same structure as mlp_fwd3.cu)
+// ------------------------------------------------------------------------------------
+constexpr int kC3Threads = 576;
+constexpr uint32_t kC3ActHi = 0, kC3ActLo = 65536;
+constexpr uint32_t kC3Ring = 131072;
+constexpr int kC3Stages = 6;
+constexpr uint32_t kC3Bars = kC3Ring + kC3Stages * kBlockBytes;       // 229376
+constexpr uint32_t kC3TmemSlot = kC3Bars + 192;
+constexpr uint32_t kC3Smem = kC3Bars + 256;
+constexpr int kC3NumBlocks = 8 + 8 * 16;                              // step 0: K = 128, steps 1-8: K = 256
+
+// block b of the chain stream: [256 rows (input feature j) x 16 k (output feature n)] of layer L = 9 - step
+__global__ void __launch_bounds__(256)
+pack_bwd_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
+    const int b = blockIdx.x;
+    const int step = b < 8 ? 0 : 1 + (b - 8) / 16, kb = b < 8 ? b : (b - 8) % 16;
+    const int L = 9 - step;
+    const float* W = p.w[L];
+    const int ld = p.ld[L], col0 = (L == 5) ? 63 : 0;
+    uint8_t* dst = stream + (size_t)b * kBlockBytes;
+    for (int u = threadIdx.x; u < 512; u += 256) {
+        const int r = u & 255, kg = u >> 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = W[(size_t)(kb * 16 + kg * 8 + e) * ld + col0 + r];
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_pack2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+        size_t off = (size_t)kg * 4096 + (size_t)r * 16;
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dst + kBlockHalfBytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+__device__ __forceinline__ void st_global_v4g(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8g(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// one k-group of G: hi/lo words to the SMEM operand tile (optional) and to the gradient record
+__device__ __forceinline__ void emit_g(bool to_smem, uint32_t hi_base, uint32_t lo_base, uint8_t* rec_hi, size_t lo_off,
+                                       uint32_t row, uint32_t kg, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    const uint32_t off = kg * kLBO + row * 16;
+    if (to_smem) {
+        st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+        st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
+    }
+    st_global_v4g(rec_hi + off, h[0], h[1], h[2], h[3]);
+    st_global_v4g(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(kC3Threads, 1)
+mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
+                     const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
+                     uint8_t* __restrict__ grads) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kC3Bars, bar_empty = bar_full + 8 * kC3Stages;
+    const uint32_t bar_dfull = bar_empty + 8 * kC3Stages;       // [2]
+    const uint32_t bar_aready = bar_dfull + 16;                  // [8]  16 arrivals each (one per epilogue warp)
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kC3TmemSlot);
+    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kC3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_dfull, 1); mbar_init(bar_dfull + 8, 1);
+        for (int k = 0; k < 8; ++k) mbar_init(bar_aready + 8 * k, 16);
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(sbase + kC3TmemSlot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // ===== weight loader =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int b = 0; b < kC3NumBlocks; ++b, ++it) {
+                    const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
+                    bulk_g2s(sbase + kC3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
+                }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
+        constexpr uint32_t idesc = instr_desc(128, 256);
+        const uint64_t b256 = smem_desc_any(sbase + kC3Ring, 4096, 128);
+        const uint64_t act_hi = smem_desc(sbase + kC3ActHi), act_lo = smem_desc(sbase + kC3ActLo);
+        constexpr uint32_t kStep = 2 * (kLBO >> 4);
+        uint32_t it = 0;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+#pragma unroll 1
+            for (int step = 0; step < 9; ++step) {
+                const uint32_t d = tmem + (uint32_t)(step & 1) * 256;
+                const int nb = step == 0 ? 8 : 16;
+#pragma unroll 1
+                for (int j = 0; j < nb; ++j, ++it) {
+                    if (!(j & 1)) {
+                        const int kb = j >> 1;
+                        const uint32_t aph = kb < 4 ? (uint32_t)(tl * 9 + step) & 1 : (uint32_t)(tl * 8 + step - 1) & 1;
+                        mbar_wait(bar_aready + 8 * kb, aph);
+                    }
+                    const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
+                        const uint64_t ah = act_hi + (uint64_t)(j * kStep), al = act_lo + (uint64_t)(j * kStep);
+                        umma_f16(d, ah, bh, idesc, j == 0 ? 0u : 1u);
+                        umma_f16(d, ah, bl, idesc, 1u);
+                        umma_f16(d, al, bh, idesc, 1u);
+                        umma_commit(bar_empty + 8 * s);
+                        if (j + 1 == nb) umma_commit(bar_dfull + 8 * (step & 1));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== prologue + epilogue warps: thread = (row, p); per 32-column k-block it owns columns 8p..8p+7 =====
+        const int q = warp & 3, p = warp >> 2;
+        const uint32_t row = (uint32_t)(q * 32 + lane);
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t ah = sbase + kC3ActHi, al = sbase + kC3ActLo;
+        const float scale = grad_scale(amax_bits);
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int grow = tile * (int)kRows + (int)row;
+            const bool valid = grow < n_points;
+            const uint8_t* arec = acts + (size_t)tile * kTileBytes;
+            uint8_t* grec = grads + (size_t)tile * kGTileBytes;
+            float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
+            dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+            // G9 = (d_rgb W_rgb) * [hv > 0]: four k-blocks of 32 columns
+#pragma unroll 1
+            for (uint32_t kb = 0; kb < 4; ++kb) {
+                const uint32_t kg = kb * 4 + (uint32_t)p, c = kg * 8;
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(arec + kSlotHV + (size_t)kg * 2048 + row * 16));
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float gsum = dr.x * __ldg(misc + kMiscRgbW + c + j) + dr.y * __ldg(misc + kMiscRgbW + 128 + c + j) +
+                                 dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
+                    uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
+                    v[j] = hb ? clamp_h(gsum) : 0.f;
+                }
+                emit_g(true, ah, al, grec + g_slot(9), 32768, row, kg, v);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_aready + 8 * kb);
+            }
+#pragma unroll 1
+            for (int step = 0; step < 9; ++step) {
+                const int L = 9 - step;                           // D = gradient w.r.t. the input of layer L = G_{L-1} before masking
+                mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1);
+                tc_fence_after();
+                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;      // hi half of h_{L-1} (L <= 8)
+                uint8_t* gslot = grec + g_slot(L - 1);
+                const uint32_t dcol = t_lane + (uint32_t)(step & 1) * 256 + (uint32_t)p * 8;
+                const bool feed = step < 8;                       // G0 has no consumer in this kernel
+#pragma unroll 1
+                for (uint32_t kb = 0; kb < 8; kb += 2) {
+                    float v[16];
+                    uint4 m[2];
+                    if (L != 9) {
+                        m[0] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(kb * 4 + p) * 2048 + row * 16));
+                        m[1] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)((kb + 1) * 4 + p) * 2048 + row * 16));
+                    }
+                    tmem_ld8g(dcol + kb * 32, v);
+                    tmem_ld8g(dcol + kb * 32 + 32, v + 8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t kg = (kb + u) * 4 + (uint32_t)p, c = kg * 8;
+                        float* w = v + 8 * u;
+                        if (L == 8) {                             // + d_sigma * alpha_linear.weight
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c)), a1 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + 4));
+                            w[0] = fmaf(dr.w, a0.x, w[0]); w[1] = fmaf(dr.w, a0.y, w[1]); w[2] = fmaf(dr.w, a0.z, w[2]); w[3] = fmaf(dr.w, a0.w, w[3]);
+                            w[4] = fmaf(dr.w, a1.x, w[4]); w[5] = fmaf(dr.w, a1.y, w[5]); w[6] = fmaf(dr.w, a1.z, w[6]); w[7] = fmaf(dr.w, a1.w, w[7]);
+                        }
+                        if (L != 9) {
+                            const uint32_t mw[4] = {m[u].x, m[u].y, m[u].z, m[u].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
+                                w[j] = hb ? clamp_h(w[j]) : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = clamp_h(w[j]);
+                        }
+                        emit_g(feed, ah, al, gslot, 65536, row, kg, w);
+                        if (feed) {
+                            fence_proxy_async();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------
@@ -605,6 +832,12 @@ int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaSt
     CNERF_LAUNCH_CHECK("pack_bwd_weights_kernel");
     return CNERF_OK;
 }
+int bwd_stream3_blocks() { return kC3NumBlocks; }
+int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st) {
+    pack_bwd_weights3_kernel<<<kC3NumBlocks, 256, 0, st>>>(p, stream);
+    CNERF_LAUNCH_CHECK("pack_bwd_weights3_kernel");
+    return CNERF_OK;
+}
 }  // namespace cnerf
 
 extern "C" int64_t cnerf_mlp_grads_bytes(int64_t n_points) { return ceil_div64(n_points, kRows) * (int64_t)kGTileBytes; }
@@ -645,6 +878,7 @@ int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, vo
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
         attr_set = true;
@@ -677,6 +911,13 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
+    static int impl = 0;
+    if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
+    if (impl == 3) {
+        mlp_bwd_data3_kernel<<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+        CNERF_LAUNCH_CHECK("mlp_bwd_data3_kernel");
+        return CNERF_OK;
+    }
     mlp_bwd_data_kernel<<<c.grid, kThreads, kSmemTotal, c.st>>>(w->stream_bwd, w->misc, d_raw, c.a, c.amax, n_points, c.g);
     CNERF_LAUNCH_CHECK("mlp_bwd_data_kernel");
     return CNERF_OK;

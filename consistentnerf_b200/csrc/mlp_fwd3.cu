@@ -1,0 +1,413 @@
+// K2+K3 fused forward, third generation: N=256 MMAs, double-buffered accumulators, k-block pipelining.
+//
+// Measured on B200 (scripts/umma_rate.py): one tcgen05.mma M=128 x N=256 x K=16 runs at 128-138 cycles (93-100 % of
+// the tensor pipe) no matter what else the issuing warp does, whereas N=128 instructions are issue bound
+// (90-150 cycles for 64 cycles of work).  So every 256-wide layer is issued as N=256 instructions:
+//
+//   TMEM   two 256-column fp32 accumulators; layer L accumulates into D[L & 1]
+//   SMEM   A operand: activations of the current layer (K=256, fp16 hi/lo, 128 KB) + encoding tile (32 KB),
+//          4-stage ring of 16 KB weight blocks ([256 out-rows x 16 k], hi 8 KB + lo 8 KB)
+//
+// The epilogue of layer L (16 warps) walks the accumulator k-block by k-block (32 columns of D = one 32-wide k-block
+// of the next layer's A operand) and signals each finished k-block through its own mbarrier; the MMA warp starts
+// layer L+1 on k-block 0 while the epilogue is still converting k-blocks 1..7 -- it writes the OTHER accumulator, so
+// the only serialisation left is the first k-block.  The training variant writes the activation record with
+// coalesced 16-byte global stores straight from the epilogue registers.
+#include "mlp_layout.cuh"
+
+namespace cnerf {
+
+__device__ unsigned long long g_prof3[16];
+__device__ int g_prof3_on;
+#define PROF_T0() long long pt0__ = g_prof3_on ? clock64() : 0
+#define PROF_ADD(var) do { if (g_prof3_on) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
+
+constexpr int k3Threads = 576;                           // 16 epilogue warps + loader warp + MMA warp
+constexpr uint32_t k3ActHi = 0, k3ActLo = 65536;         // 32 k-groups x 2048 B each
+constexpr uint32_t k3EmbHi = 131072, k3EmbLo = 147456;   // 8 k-groups each; k-groups 4-7 of the hi half double as scratch
+constexpr uint32_t k3SAlpha = k3EmbHi + 8192;            // float[4][128]      (valid from layer 7 on)
+constexpr uint32_t k3SRgb = k3SAlpha + 2048;             // float[3][3][128]   (layer 9)
+constexpr uint32_t k3Ring = 163840;
+constexpr int k3Stages = 4;
+constexpr uint32_t k3Bars = k3Ring + k3Stages * kBlockBytes;      // 229376
+constexpr uint32_t k3TmemSlot = k3Bars + 192;
+constexpr uint32_t k3Smem = k3Bars + 256;
+constexpr int k3NumBlocks = 4 + 16 * 4 + 20 + 16 * 3 + 9;         // 145
+
+// ------------------------------------------------------------------------------------
+// weight stream: blocks in consumption order
+//   layers 0-8: [256 rows x 16 k] blocks, element (n, k) at (k/8)*4096 + n*16 + (k%8)*2 (hi), +8192 (lo)
+//   layer 9   : [128 rows x 32 k] blocks, element (n, k) at (k/8)*2048 + n*16 + (k%8)*2 (hi), +8192 (lo)
+// ------------------------------------------------------------------------------------
+struct Blk3 { int layer, src_k0, kvalid; };
+
+__device__ __forceinline__ Blk3 block3_info(int b) {
+    // layer 0: 4 blocks; 1-4: 16 each; 5: 4 + 16; 6-8: 16 each; 9: 8 + 1
+    if (b < 4) return {0, 16 * b, b == 3 ? 15 : 16};
+    b -= 4;
+    if (b < 64) return {1 + b / 16, 16 * (b % 16), 16};
+    b -= 64;
+    if (b < 4) return {5, 16 * b, b == 3 ? 15 : 16};
+    b -= 4;
+    if (b < 16) return {5, 63 + 16 * b, 16};
+    b -= 16;
+    if (b < 48) return {6 + b / 16, 16 * (b % 16), 16};
+    b -= 48;
+    if (b < 8) return {9, 32 * b, 32};
+    return {9, 256, 27};
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
+    const Blk3 bi = block3_info(blockIdx.x);
+    const float* W = p.w[bi.layer];
+    const int ld = p.ld[bi.layer];
+    uint8_t* dst = stream + (size_t)blockIdx.x * kBlockBytes;
+    const int rows = bi.layer == 9 ? 128 : 256, kgs = bi.layer == 9 ? 4 : 2;
+    for (int u = threadIdx.x; u < rows * kgs; u += 256) {
+        const int n = u % rows, kg = u / rows;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int k = kg * 8 + e;
+            v[e] = (k < bi.kvalid) ? W[(size_t)n * ld + bi.src_k0 + k] : 0.f;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_pack2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+        size_t off = (size_t)kg * rows * 16 + (size_t)n * 16;
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dst + kBlockHalfBytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_v4_(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// 8 fp32 of one k-group -> hi/lo words into the SMEM operand tile and (training) the global record
+template <bool kSave>
+__device__ __forceinline__ void emit_kgroup(uint32_t hi_base, uint32_t lo_base, uint8_t* rec_hi, size_t lo_off, uint32_t row,
+                                            uint32_t kg, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    const uint32_t off = kg * kLBO + row * 16;
+    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
+    if (kSave) {
+        st_global_v4_(rec_hi + off, h[0], h[1], h[2], h[3]);
+        st_global_v4_(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
+    }
+}
+
+template <int J>
+__device__ __forceinline__ float enc_col3(const float (&x)[3], int width) {
+    if (J >= width) return 0.f;
+    if (J < 3) return x[J];
+    constexpr int b = (J - 3) / 3, c = (J - 3) % 3, oct = b / 2;
+    float arg = x[c] * (float)(1 << oct);
+    return (b & 1) ? cosf(arg) : sinf(arg);
+}
+template <int J0>
+__device__ __forceinline__ void enc8(const float (&x)[3], int width, float* v) {
+    v[0] = enc_col3<J0 + 0>(x, width); v[1] = enc_col3<J0 + 1>(x, width); v[2] = enc_col3<J0 + 2>(x, width);
+    v[3] = enc_col3<J0 + 3>(x, width); v[4] = enc_col3<J0 + 4>(x, width); v[5] = enc_col3<J0 + 5>(x, width);
+    v[6] = enc_col3<J0 + 6>(x, width); v[7] = enc_col3<J0 + 7>(x, width);
+}
+
+// ------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------
+template <bool kSave>
+__global__ void __launch_bounds__(k3Threads, 1)
+mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
+                  const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
+                  uint8_t* __restrict__ acts) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + k3Bars, bar_empty = bar_full + 8 * k3Stages;
+    const uint32_t bar_dfull = bar_empty + 8 * k3Stages;        // [2]  accumulator D[i] complete
+    const uint32_t bar_aready = bar_dfull + 16;                  // [8]  A k-block written (16 warp arrivals)
+    const uint32_t bar_eready = bar_aready + 64;                 //      encoding tile written (16 warp arrivals)
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k3TmemSlot);
+    float* s_alpha = reinterpret_cast<float*>(smem + k3SAlpha);
+    float* s_rgb = reinterpret_cast<float*>(smem + k3SRgb);
+    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < k3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_dfull, 1); mbar_init(bar_dfull + 8, 1);
+        for (int k = 0; k < 8; ++k) mbar_init(bar_aready + 8 * k, 16);      // one arrival per epilogue warp
+        mbar_init(bar_eready, 16);
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(sbase + k3TmemSlot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // ===== weight loader =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int b = 0; b < k3NumBlocks; ++b, ++it) {
+                    const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
+                    bulk_g2s(sbase + k3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
+                }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer: the whole warp walks the static program (warp-uniform control flow), one elected lane issues =====
+        constexpr uint32_t idesc256 = instr_desc(128, 256), idesc128 = instr_desc(128, 128);
+        const uint64_t b256 = smem_desc_any(sbase + k3Ring, 4096, 128);          // + stage*1024 ; lo: +512
+        const uint64_t b128 = smem_desc(sbase + k3Ring);
+        const uint64_t act_hi = smem_desc(sbase + k3ActHi), act_lo = smem_desc(sbase + k3ActLo);
+        const uint64_t emb_hi = smem_desc(sbase + k3EmbHi), emb_lo = smem_desc(sbase + k3EmbLo);
+        constexpr uint32_t kStep = 2 * (kLBO >> 4);                               // two k-groups = one K=16 step of the A tile
+        uint32_t it = 0;
+        long long pw_a = 0, pw_full = 0, pw_e = 0, p_start = g_prof3_on ? clock64() : 0;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            { PROF_T0(); mbar_wait(bar_eready, (uint32_t)tl & 1); PROF_ADD(pw_e); }
+#pragma unroll 1
+            for (int layer = 0; layer < 9; ++layer) {
+                const uint32_t d = tmem + (uint32_t)(layer & 1) * 256;
+                const int n_emb = (layer == 0 || layer == 5) ? 4 : 0, n_act = layer == 0 ? 0 : 16;
+                const uint32_t aph = (uint32_t)(tl * 9 + layer - 1) & 1;
+#pragma unroll 1
+                for (int j = 0; j < n_emb + n_act; ++j, ++it) {
+                    const bool is_act = j >= n_emb;
+                    const int ja = j - n_emb;
+                    if (is_act && !(ja & 1)) { PROF_T0(); mbar_wait(bar_aready + 8 * (ja >> 1), aph); PROF_ADD(pw_a); }
+                    const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
+                    { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
+                        const uint64_t ah = (is_act ? act_hi + (uint64_t)(ja * kStep) : emb_hi + (uint64_t)(j * kStep));
+                        const uint64_t al = (is_act ? act_lo + (uint64_t)(ja * kStep) : emb_lo + (uint64_t)(j * kStep));
+                        umma_f16(d, ah, bh, idesc256, j == 0 ? 0u : 1u);
+                        umma_f16(d, ah, bl, idesc256, 1u);
+                        umma_f16(d, al, bh, idesc256, 1u);
+                        umma_commit(bar_empty + 8 * s);
+                        if (j + 1 == n_emb + n_act) umma_commit(bar_dfull + 8 * (layer & 1));
+                    }
+                    __syncwarp();
+                }
+            }
+            {   // views layer: N = 128, [128 x 32] blocks, accumulator D[1] columns 256..383
+                const uint32_t d = tmem + 256;
+                const uint32_t aph = (uint32_t)(tl * 9 + 8) & 1;
+#pragma unroll 1
+                for (int j = 0; j < 9; ++j, ++it) {
+                    if (j < 8) { PROF_T0(); mbar_wait(bar_aready + 8 * j, aph); PROF_ADD(pw_a); }
+                    const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
+                    { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t bh = b128 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
+                        const uint64_t ah = j < 8 ? act_hi + (uint64_t)(j * 2 * kStep) : emb_hi;
+                        const uint64_t al = j < 8 ? act_lo + (uint64_t)(j * 2 * kStep) : emb_lo;
+                        umma_f16(d, ah, bh, idesc128, j == 0 ? 0u : 1u);
+                        umma_f16(d, ah, bl, idesc128, 1u);
+                        umma_f16(d, al, bh, idesc128, 1u);
+                        umma_f16(d, ah + kStep, bh + kStep, idesc128, 1u);
+                        umma_f16(d, ah + kStep, bl + kStep, idesc128, 1u);
+                        umma_f16(d, al + kStep, bh + kStep, idesc128, 1u);
+                        umma_commit(bar_empty + 8 * s);
+                        if (j == 8) umma_commit(bar_dfull + 8);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (g_prof3_on && lane == 0) {
+            atomicAdd(&g_prof3[0], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_prof3[1], (unsigned long long)pw_a); atomicAdd(&g_prof3[2], (unsigned long long)pw_e);
+            atomicAdd(&g_prof3[3], (unsigned long long)pw_full);
+        }
+    } else {
+        // ===== prologue + epilogue warps: thread = (row, p); per k-block of 32 columns it owns columns 8p..8p+7 =====
+        const int q = warp & 3, p = warp >> 2;
+        const uint32_t row = (uint32_t)(q * 32 + lane);
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t ah = sbase + k3ActHi, al = sbase + k3ActLo, eh = sbase + k3EmbHi, el = sbase + k3EmbLo;
+        long long pw_d = 0, p_start = g_prof3_on ? clock64() : 0;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int grow = tile * (int)kRows + (int)row;
+            const bool valid = grow < n_points;
+            uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
+            {   // point encoding: k-groups 2p, 2p+1 of the 64-wide tile
+                float x[3] = {0.f, 0.f, 0.f};
+                if (valid) { x[0] = pts[3 * (size_t)grow]; x[1] = pts[3 * (size_t)grow + 1]; x[2] = pts[3 * (size_t)grow + 2]; }
+                float v[8];
+                uint8_t* rh = rec + kSlotE;
+                if (p == 0)      { enc8<0>(x, 63, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 0, v); enc8<8>(x, 63, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 1, v); }
+                else if (p == 1) { enc8<16>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 2, v); enc8<24>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 3, v); }
+                else if (p == 2) { enc8<32>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 4, v); enc8<40>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 5, v); }
+                else             { enc8<48>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 6, v); enc8<56>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 7, v); }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_eready);
+            }
+            float alpha_acc = 0.f;
+#pragma unroll 1
+            for (int layer = 0; layer < 9; ++layer) {
+                { PROF_T0(); mbar_wait(bar_dfull + 8 * (layer & 1), (uint32_t)(tl * 5 + (layer >> 1)) & 1); PROF_ADD(pw_d); }
+                tc_fence_after();
+                if (layer == 5) {
+                    // every MMA of layer 5 (the last reader of the point encoding) is done: the tile now takes the
+                    // direction encoding, one k-group per column part; published by this layer's a_ready arrivals
+                    float dvec[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
+                        int ray = min(grow / n_samples, n_rays - 1);
+                        dvec[0] = viewdirs[3 * (size_t)ray]; dvec[1] = viewdirs[3 * (size_t)ray + 1]; dvec[2] = viewdirs[3 * (size_t)ray + 2];
+                    }
+                    float v[8];
+                    uint8_t* rh = rec + kSlotV;
+                    if (p == 0)      { enc8<0>(dvec, 27, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 0, v); }
+                    else if (p == 1) { enc8<8>(dvec, 27, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 1, v); }
+                    else if (p == 2) { enc8<16>(dvec, 27, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 2, v); }
+                    else             { enc8<24>(dvec, 27, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 3, v); }
+                }
+                const float* bias = misc + kMiscBias + layer * 256;
+                const bool relu = layer != 8;
+                const uint32_t dcol = t_lane + (uint32_t)(layer & 1) * 256 + (uint32_t)p * 8;
+                uint8_t* slot = rec + (layer < 8 ? kSlotH0 + (size_t)layer * 131072 : kSlotF);
+#pragma unroll 1
+                for (uint32_t kb = 0; kb < 8; kb += 2) {
+                    float v[16];
+                    tmem_ld8(dcol + kb * 32, v);
+                    tmem_ld8(dcol + kb * 32 + 32, v + 8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t c = (kb + u) * 32 + (uint32_t)p * 8;
+                        float* w = v + 8 * u;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+                        w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w; w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float t = relu ? fmaxf(w[j], 0.f) : fmaxf(w[j], -65504.f);
+                            w[j] = fminf(t, 65504.f);
+                        }
+                        if (layer == 7) {
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c)), a1 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + 4));
+                            alpha_acc = fmaf(w[0], a0.x, alpha_acc); alpha_acc = fmaf(w[1], a0.y, alpha_acc);
+                            alpha_acc = fmaf(w[2], a0.z, alpha_acc); alpha_acc = fmaf(w[3], a0.w, alpha_acc);
+                            alpha_acc = fmaf(w[4], a1.x, alpha_acc); alpha_acc = fmaf(w[5], a1.y, alpha_acc);
+                            alpha_acc = fmaf(w[6], a1.z, alpha_acc); alpha_acc = fmaf(w[7], a1.w, alpha_acc);
+                        }
+                        emit_kgroup<kSave>(ah, al, slot, 65536, row, (kb + u) * 4 + (uint32_t)p, w);
+                        fence_proxy_async();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
+                    }
+                }
+                if (layer == 7) s_alpha[p * 128 + row] = alpha_acc;
+            }
+            {   // views layer: ReLU, then rgb_linear as an fp32 dot product; 32 of the 128 columns per thread
+                { PROF_T0(); mbar_wait(bar_dfull + 8, (uint32_t)(tl * 5 + 4) & 1); PROF_ADD(pw_d); }
+                tc_fence_after();
+                const float* bias = misc + kMiscBias + 9 * 256;
+                const uint32_t c = (uint32_t)p * 32;
+                float v[32];
+                tmem_ld32(t_lane + 256 + c, v);
+                tmem_ld_wait();
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float hv = fmaxf(v[j] + __ldg(bias + c + j), 0.f);
+                    r0 = fmaf(hv, __ldg(misc + kMiscRgbW + c + j), r0);
+                    r1 = fmaf(hv, __ldg(misc + kMiscRgbW + 128 + c + j), r1);
+                    r2 = fmaf(hv, __ldg(misc + kMiscRgbW + 256 + c + j), r2);
+                    v[j] = fminf(hv, 65504.f);
+                }
+                if (kSave) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_pack2(v[8 * k4 + 2 * i], v[8 * k4 + 2 * i + 1], h[i], l[i]);
+                        uint8_t* o = rec + kSlotHV + (size_t)((c >> 3) + k4) * 2048 + row * 16;
+                        st_global_v4_(o, h[0], h[1], h[2], h[3]);
+                        st_global_v4_(o + 32768, l[0], l[1], l[2], l[3]);
+                    }
+                }
+                if (p > 0) { float* o = s_rgb + (p - 1) * 384; o[row] = r0; o[128 + row] = r1; o[256 + row] = r2; }
+                named_bar_sync(1, 512);
+                if (p == 0 && valid) {
+                    float4 o;
+                    o.x = r0 + s_rgb[row] + s_rgb[384 + row] + s_rgb[768 + row] + __ldg(misc + kMiscRgbB);
+                    o.y = r1 + s_rgb[128 + row] + s_rgb[512 + row] + s_rgb[896 + row] + __ldg(misc + kMiscRgbB + 1);
+                    o.z = r2 + s_rgb[256 + row] + s_rgb[640 + row] + s_rgb[1024 + row] + __ldg(misc + kMiscRgbB + 2);
+                    o.w = s_alpha[row] + s_alpha[128 + row] + s_alpha[256 + row] + s_alpha[384 + row] + __ldg(misc + kMiscAlphaB);
+                    *reinterpret_cast<float4*>(raw + 4 * (size_t)grow) = o;
+                }
+                tc_fence_before();
+                named_bar_sync(1, 512);      // the scratch aliases the encoding tile the next prologue rewrites
+            }
+        }
+        if (g_prof3_on && lane == 0 && warp == 0) {
+            atomicAdd(&g_prof3[8], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_prof3[9], (unsigned long long)pw_d);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
+}
+
+int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st) {
+    pack_weights3_kernel<<<k3NumBlocks, 256, 0, st>>>(p, stream3);
+    CNERF_LAUNCH_CHECK("pack_weights3_kernel");
+    return CNERF_OK;
+}
+int stream3_blocks() { return k3NumBlocks; }
+
+int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused3_kernel)");
+        attr_set = true;
+    }
+    const int tiles = ceil_div(n_points, (int)kRows);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    if (acts) mlp_fused3_kernel<true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
+    else mlp_fused3_kernel<false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
+    CNERF_LAUNCH_CHECK("mlp_fused3_kernel");
+    return CNERF_OK;
+}
+
+}  // namespace cnerf
+
+// Debug: in-kernel phase profile of mlp_fused3_kernel (cycles summed over CTAs):
+//  [0] MMA warp total  [1] wait A k-blocks  [2] wait encoding  [3] wait weights   [8] epilogue total  [9] wait D
+extern "C" int cnerf_debug_profile3(int enable, unsigned long long* out16) {
+    using namespace cnerf;
+    unsigned long long zero[16] = {0};
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_prof3, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3, zero, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3_on, &enable, sizeof(int));
+    if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile3");
+    return CNERF_OK;
+}

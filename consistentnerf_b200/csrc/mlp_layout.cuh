@@ -58,6 +58,8 @@ constexpr uint32_t kTmemCols = 512;
 struct cnerf_weights {
     uint8_t* stream = nullptr;      // forward weight stream: packed fp16 hi/lo blocks in program order
     uint8_t* stream_bwd = nullptr;  // transposed blocks in the order the data-gradient chain consumes them
+    uint8_t* stream_bwd3 = nullptr; // chain stream of the N=256 backward kernel: [256 x 16] transposed blocks
+    uint8_t* stream3 = nullptr;     // forward stream of the N=256 kernel (mlp_fwd3.cu): [256 x 16] blocks
     float* misc = nullptr;          // biases + alpha/rgb heads (fp32)
     int num_blocks = 0, num_blocks_bwd = 0;
     int device = -1;

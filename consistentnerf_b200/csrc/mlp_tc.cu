@@ -877,6 +877,12 @@ using namespace cnerf;
 namespace cnerf {
 int upload_bwd_program_once(int* nblocks);                                   // mlp_bwd_tc.cu
 int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaStream_t st);
+int bwd_stream3_blocks();
+int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st);
+int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st);                                // mlp_fwd3.cu
+int stream3_blocks();
+int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 }
 
 static int upload_program(int* nblocks) {
@@ -900,8 +906,10 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
     cudaGetDevice(&w->device);
     cudaError_t e = cudaMalloc(&w->stream, (size_t)w->num_blocks * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd, (size_t)w->num_blocks_bwd * kBlockBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->stream3, (size_t)stream3_blocks() * kBlockBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd3, (size_t)bwd_stream3_blocks() * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->misc, kMiscFloats * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(w->stream); cudaFree(w->stream_bwd); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
+    if (e != cudaSuccess) { cudaFree(w->stream); cudaFree(w->stream_bwd); cudaFree(w->stream3); cudaFree(w->stream_bwd3); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
     *out = w;
     return CNERF_OK;
 }
@@ -910,6 +918,8 @@ extern "C" void cnerf_weights_destroy(cnerf_weights* w) {
     if (!w) return;
     cudaFree(w->stream);
     cudaFree(w->stream_bwd);
+    cudaFree(w->stream3);
+    cudaFree(w->stream_bwd3);
     cudaFree(w->misc);
     delete w;
 }
@@ -933,6 +943,8 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     pack_misc_kernel<<<ceil_div(kMiscFloats, 256), 256, 0, as_stream(stream)>>>(p, w->misc);
     CNERF_LAUNCH_CHECK("pack_misc_kernel");
     int rc = pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
+    if (rc == CNERF_OK) rc = pack_stream3(p, w->stream3, as_stream(stream));
+    if (rc == CNERF_OK) rc = pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream));
     if (rc != CNERF_OK) return rc;
     w->packed = true;
     return CNERF_OK;
@@ -948,9 +960,11 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     if (np64 == 0) return CNERF_OK;
     static bool attr_set = false;
     static bool use_v1 = false;
+    static int impl = 3;
     if (!attr_set) {
-        const char* ev = getenv("CNERF_MLP_V1");
-        use_v1 = ev && ev[0] == '1';
+        const char* ev = getenv("CNERF_MLP_IMPL");          // 1: serial SS kernel, 2: TMEM-resident N=128 halves, 3 (default): N=256
+        if (ev && ev[0] >= '1' && ev[0] <= '3') impl = ev[0] - '0';
+        use_v1 = impl == 1;
         cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
@@ -961,6 +975,8 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     int n_points = (int)np64;
     int tiles = ceil_div(n_points, (int)kRows);
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    if (impl == 3)
+        return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     if (!use_v1) {
         if (acts)
             mlp_fused2_kernel<true><<<grid, kThreads2, k2Smem, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,

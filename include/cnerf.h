@@ -224,6 +224,7 @@ int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* ma
 /* Debug aid: enable/disable the in-kernel phase profile of the fused MLP kernel and read + clear its 16 cycle
  * counters (host pointer, may be NULL).  Synchronises the device. */
 int cnerf_debug_profile(int enable, unsigned long long* out16);
+int cnerf_debug_profile3(int enable, unsigned long long* out16);
 /* Debug aid: measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */
 int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream);
 

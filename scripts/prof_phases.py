@@ -11,14 +11,14 @@ net = module_from_params(O.make_params(0, sigma_bias=0.5, **ARCH), ARCH)
 packed = net.packed_weights(); packed.refresh(dict(zip(net.spec.param_names(), [p.detach() for p in net.hot_params()])))
 n, S = 4096, 192
 pts = torch.randn(n, S, 3, device=dev); vd = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
-names = {0: "mma total", 1: "mma wait A0", 2: "mma wait A1", 3: "mma wait weights", 4: "loader wait empty", 8: "grpA total", 9: "grpA wait D", 10: "grpA wait afree", 12: "grpB total", 13: "grpB wait D"}
+names = {0: "mma total", 1: "mma wait A kblocks", 2: "mma wait enc", 3: "mma wait weights", 8: "epilogue total", 9: "epilogue wait D"}
 for mode in ("infer", "train"):
     fn = (lambda: cn.ops.fused_mlp_forward(packed, pts, vd)) if mode == "infer" else (lambda: cn.ops.fused_mlp_forward_train(packed, pts, vd))
     for _ in range(2): fn()
     out = (ctypes.c_ulonglong * 16)()
-    _lib.call("cnerf_debug_profile", 1, out)
+    _lib.call("cnerf_debug_profile3", 1, out)
     fn()
-    _lib.call("cnerf_debug_profile", 0, out)
+    _lib.call("cnerf_debug_profile3", 0, out)
     tiles = n * S / 128 / 148
     print(mode, "tiles/CTA %.1f" % tiles)
     for k, nm in names.items():
