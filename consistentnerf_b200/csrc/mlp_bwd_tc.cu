@@ -317,19 +317,14 @@ __device__ __forceinline__ void tmem_ld8g(uint32_t taddr, float* v) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
 }
-// one k-group of G: hi/lo words to the SMEM operand tile (optional) and to the gradient record
-__device__ __forceinline__ void emit_g(bool to_smem, uint32_t hi_base, uint32_t lo_base, uint8_t* rec_hi, size_t lo_off,
-                                       uint32_t row, uint32_t kg, const float* v) {
+// one k-group of G: hi/lo words into the SMEM operand tile (the MMA warp streams finished k-blocks to the record)
+__device__ __forceinline__ void emit_g(uint32_t hi_base, uint32_t lo_base, uint32_t row, uint32_t kg, const float* v) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
     const uint32_t off = kg * kLBO + row * 16;
-    if (to_smem) {
-        st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
-        st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
-    }
-    st_global_v4g(rec_hi + off, h[0], h[1], h[2], h[3]);
-    st_global_v4g(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
+    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
 }
 
 __global__ void __launch_bounds__(kC3Threads, 1)
@@ -342,6 +337,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
     const uint32_t bar_full = sbase + kC3Bars, bar_empty = bar_full + 8 * kC3Stages;
     const uint32_t bar_dfull = bar_empty + 8 * kC3Stages;       // [2]
     const uint32_t bar_aready = bar_dfull + 16;                  // [8]  16 arrivals each (one per epilogue warp)
+    const uint32_t bar_sdone = bar_aready + 64;                  //      the tile's last G stores have left shared memory
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kC3TmemSlot);
     const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
 
@@ -349,6 +345,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         for (int s = 0; s < kC3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_dfull, 1); mbar_init(bar_dfull + 8, 1);
         for (int k = 0; k < 8; ++k) mbar_init(bar_aready + 8 * k, 16);
+        mbar_init(bar_sdone, 1);
         fence_barrier_init();
     }
     if (warp == 17) tmem_alloc(sbase + kC3TmemSlot, 512);
@@ -378,6 +375,15 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         uint32_t it = 0;
         int tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            uint8_t* grec = grads + (size_t)tile * kGTileBytes;
+            // every k-block of an operand tile (G of some layer) is streamed to the gradient record as soon as it is final
+            auto store_kblock = [&](int layer, int kb) {
+                uint8_t* slot = grec + g_slot(layer);
+                const size_t lo_off = layer == 9 ? 32768 : 65536;
+                bulk_s2g(slot + (size_t)kb * 8192, sbase + kC3ActHi + kb * 8192, 8192);
+                bulk_s2g(slot + lo_off + (size_t)kb * 8192, sbase + kC3ActLo + kb * 8192, 8192);
+                bulk_commit();
+            };
 #pragma unroll 1
             for (int step = 0; step < 9; ++step) {
                 const uint32_t d = tmem + (uint32_t)(step & 1) * 256;
@@ -386,8 +392,10 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                 for (int j = 0; j < nb; ++j, ++it) {
                     if (!(j & 1)) {
                         const int kb = j >> 1;
-                        const uint32_t aph = kb < 4 ? (uint32_t)(tl * 9 + step) & 1 : (uint32_t)(tl * 8 + step - 1) & 1;
+                        const uint32_t aph = kb < 4 ? (uint32_t)(tl * 10 + step) & 1 : (uint32_t)(tl * 9 + step - 1) & 1;
                         mbar_wait(bar_aready + 8 * kb, aph);
+                        if (elect_one()) store_kblock(9 - step, kb);
+                        __syncwarp();
                     }
                     const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
                     mbar_wait(bar_full + 8 * s, ph);
@@ -399,12 +407,26 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                         umma_f16(d, ah, bl, idesc, 1u);
                         umma_f16(d, al, bh, idesc, 1u);
                         umma_commit(bar_empty + 8 * s);
-                        if (j + 1 == nb) umma_commit(bar_dfull + 8 * (step & 1));
+                        if (j + 1 == nb) {
+                            bulk_wait_read0();                  // the epilogue overwrites the operand tile once it sees this step done
+                            umma_commit(bar_dfull + 8 * (step & 1));
+                        }
                     }
                     __syncwarp();
                 }
             }
+            // G0, written by the last epilogue, has no consumer here: store it and release the tile to the next prologue
+#pragma unroll 1
+            for (int kb = 0; kb < 8; ++kb) {
+                mbar_wait(bar_aready + 8 * kb, kb < 4 ? (uint32_t)(tl * 10 + 9) & 1 : (uint32_t)(tl * 9 + 8) & 1);
+                if (elect_one()) store_kblock(0, kb);
+                __syncwarp();
+            }
+            if (elect_one()) { bulk_wait_read0(); mbar_arrive(bar_sdone); }
+            __syncwarp();
         }
+        if (elect_one()) bulk_wait0();
+        __syncwarp();
     } else {
         // ===== prologue + epilogue warps: thread = (row, p); per 32-column k-block it owns columns 8p..8p+7 =====
         const int q = warp & 3, p = warp >> 2;
@@ -417,10 +439,10 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
             const int grow = tile * (int)kRows + (int)row;
             const bool valid = grow < n_points;
             const uint8_t* arec = acts + (size_t)tile * kTileBytes;
-            uint8_t* grec = grads + (size_t)tile * kGTileBytes;
             float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
             dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+            if (tl > 0) mbar_wait(bar_sdone, (uint32_t)(tl - 1) & 1);        // the previous tile's G0 has left the operand tile
             // G9 = (d_rgb W_rgb) * [hv > 0]: four k-blocks of 32 columns
 #pragma unroll 1
             for (uint32_t kb = 0; kb < 4; ++kb) {
@@ -435,7 +457,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                     uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
                     v[j] = hb ? clamp_h(gsum) : 0.f;
                 }
-                emit_g(true, ah, al, grec + g_slot(9), 32768, row, kg, v);
+                emit_g(ah, al, row, kg, v);
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
@@ -447,9 +469,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                 mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1);
                 tc_fence_after();
                 const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;      // hi half of h_{L-1} (L <= 8)
-                uint8_t* gslot = grec + g_slot(L - 1);
                 const uint32_t dcol = t_lane + (uint32_t)(step & 1) * 256 + (uint32_t)p * 8;
-                const bool feed = step < 8;                       // G0 has no consumer in this kernel
 #pragma unroll 1
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
                     float v[16];
@@ -481,13 +501,11 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
 #pragma unroll
                             for (int j = 0; j < 8; ++j) w[j] = clamp_h(w[j]);
                         }
-                        emit_g(feed, ah, al, gslot, 65536, row, kg, w);
-                        if (feed) {
-                            fence_proxy_async();
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
-                        }
+                        emit_g(ah, al, row, kg, w);
+                        fence_proxy_async();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
                     }
                 }
             }

@@ -24,37 +24,40 @@ __device__ int g_prof3_on;
 
 constexpr int k3Threads = 576;                           // 16 epilogue warps + loader warp + MMA warp
 constexpr uint32_t k3ActHi = 0, k3ActLo = 65536;         // 32 k-groups x 2048 B each
-constexpr uint32_t k3EmbHi = 131072, k3EmbLo = 147456;   // 8 k-groups each; k-groups 4-7 of the hi half double as scratch
-constexpr uint32_t k3SAlpha = k3EmbHi + 8192;            // float[4][128]      (valid from layer 7 on)
+constexpr uint32_t k3EmbHi = 131072, k3EmbLo = 147456;   // 8 k-groups each; k-groups 4-7 of the LO half double as scratch
+constexpr uint32_t k3SAlpha = k3EmbLo + 8192;            // float[4][128]      (valid from layer 7 on)
 constexpr uint32_t k3SRgb = k3SAlpha + 2048;             // float[3][3][128]   (layer 9)
 constexpr uint32_t k3Ring = 163840;
 constexpr int k3Stages = 4;
 constexpr uint32_t k3Bars = k3Ring + k3Stages * kBlockBytes;      // 229376
 constexpr uint32_t k3TmemSlot = k3Bars + 192;
 constexpr uint32_t k3Smem = k3Bars + 256;
-constexpr int k3NumBlocks = 4 + 16 * 4 + 20 + 16 * 3 + 9;         // 145
+constexpr int k3NumBlocks = 4 + 17 * 4 + 20 + 17 * 3 + 9;         // 152 (one bias block for every layer without an encoding block)
 
 // ------------------------------------------------------------------------------------
 // weight stream: blocks in consumption order
 //   layers 0-8: [256 rows x 16 k] blocks, element (n, k) at (k/8)*4096 + n*16 + (k%8)*2 (hi), +8192 (lo)
 //   layer 9   : [128 rows x 32 k] blocks, element (n, k) at (k/8)*2048 + n*16 + (k%8)*2 (hi), +8192 (lo)
+// Biases ride on the tensor core: the padding column of the encoding tile (column 63 of the point encoding, column 31
+// of the direction encoding) holds 1.0 and the matching weight column holds the bias.  Layers whose input has no
+// encoding part get one extra block that multiplies encoding columns 48-63 with [0 ... 0, bias].
 // ------------------------------------------------------------------------------------
-struct Blk3 { int layer, src_k0, kvalid; };
+struct Blk3 { int layer, src_k0, kvalid, bias_k; };       // bias_k: column of the block that carries the bias (-1: none)
 
 __device__ __forceinline__ Blk3 block3_info(int b) {
-    // layer 0: 4 blocks; 1-4: 16 each; 5: 4 + 16; 6-8: 16 each; 9: 8 + 1
-    if (b < 4) return {0, 16 * b, b == 3 ? 15 : 16};
+    // layer 0: 4 blocks; 1-4: 16 + bias; 5: 4 + 16; 6-8: 16 + bias; 9: 8 + 1
+    if (b < 4) return {0, 16 * b, b == 3 ? 15 : 16, b == 3 ? 15 : -1};
     b -= 4;
-    if (b < 64) return {1 + b / 16, 16 * (b % 16), 16};
-    b -= 64;
-    if (b < 4) return {5, 16 * b, b == 3 ? 15 : 16};
+    if (b < 68) { int l = 1 + b / 17, j = b % 17; return j < 16 ? Blk3{l, 16 * j, 16, -1} : Blk3{l, 0, 0, 15}; }
+    b -= 68;
+    if (b < 4) return {5, 16 * b, b == 3 ? 15 : 16, b == 3 ? 15 : -1};
     b -= 4;
-    if (b < 16) return {5, 63 + 16 * b, 16};
+    if (b < 16) return {5, 63 + 16 * b, 16, -1};
     b -= 16;
-    if (b < 48) return {6 + b / 16, 16 * (b % 16), 16};
-    b -= 48;
-    if (b < 8) return {9, 32 * b, 32};
-    return {9, 256, 27};
+    if (b < 51) { int l = 6 + b / 17, j = b % 17; return j < 16 ? Blk3{l, 16 * j, 16, -1} : Blk3{l, 0, 0, 15}; }
+    b -= 51;
+    if (b < 8) return {9, 32 * b, 32, -1};
+    return {9, 256, 27, 31};
 }
 
 __global__ void __launch_bounds__(256)
@@ -70,7 +73,7 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             int k = kg * 8 + e;
-            v[e] = (k < bi.kvalid) ? W[(size_t)n * ld + bi.src_k0 + k] : 0.f;
+            v[e] = (k < bi.kvalid) ? W[(size_t)n * ld + bi.src_k0 + k] : (k == bi.bias_k ? p.b[bi.layer][n] : 0.f);
         }
         uint32_t h[4], l[4];
 #pragma unroll
@@ -139,6 +142,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     const uint32_t bar_dfull = bar_empty + 8 * k3Stages;        // [2]  accumulator D[i] complete
     const uint32_t bar_aready = bar_dfull + 16;                  // [8]  A k-block written (16 warp arrivals)
     const uint32_t bar_eready = bar_aready + 64;                 //      encoding tile written (16 warp arrivals)
+    const uint32_t bar_hv = bar_eready + 8;                      //      training: views-layer output staged in SMEM
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k3TmemSlot);
     float* s_alpha = reinterpret_cast<float*>(smem + k3SAlpha);
     float* s_rgb = reinterpret_cast<float*>(smem + k3SRgb);
@@ -149,6 +153,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         mbar_init(bar_dfull, 1); mbar_init(bar_dfull + 8, 1);
         for (int k = 0; k < 8; ++k) mbar_init(bar_aready + 8 * k, 16);      // one arrival per epilogue warp
         mbar_init(bar_eready, 16);
+        mbar_init(bar_hv, 16);
         fence_barrier_init();
     }
     if (warp == 17) tmem_alloc(sbase + k3TmemSlot, 512);
@@ -181,29 +186,52 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         long long pw_a = 0, pw_full = 0, pw_e = 0, p_start = g_prof3_on ? clock64() : 0;
         int tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
             { PROF_T0(); mbar_wait(bar_eready, (uint32_t)tl & 1); PROF_ADD(pw_e); }
+            if (kSave && elect_one()) { bulk_s2g(rec + kSlotE, sbase + k3EmbHi, 32768); bulk_commit(); }
+            __syncwarp();
 #pragma unroll 1
             for (int layer = 0; layer < 9; ++layer) {
                 const uint32_t d = tmem + (uint32_t)(layer & 1) * 256;
-                const int n_emb = (layer == 0 || layer == 5) ? 4 : 0, n_act = layer == 0 ? 0 : 16;
+                const int n_emb = (layer == 0 || layer == 5) ? 4 : 0, n_act = layer == 0 ? 0 : 16, n_bias = n_emb ? 0 : 1;
+                const int nb = n_emb + n_act + n_bias;
                 const uint32_t aph = (uint32_t)(tl * 9 + layer - 1) & 1;
+                uint8_t* slot = rec + kSlotH0 + (size_t)(layer - 1) * 131072;             // A of this layer = output of layer - 1
 #pragma unroll 1
-                for (int j = 0; j < n_emb + n_act; ++j, ++it) {
-                    const bool is_act = j >= n_emb;
+                for (int j = 0; j < nb; ++j, ++it) {
+                    const bool is_act = j >= n_emb && j < n_emb + n_act;
                     const int ja = j - n_emb;
-                    if (is_act && !(ja & 1)) { PROF_T0(); mbar_wait(bar_aready + 8 * (ja >> 1), aph); PROF_ADD(pw_a); }
+                    if (is_act && !(ja & 1)) {
+                        const int kb = ja >> 1;
+                        { PROF_T0(); mbar_wait(bar_aready + 8 * kb, aph); PROF_ADD(pw_a); }
+                        if (kSave && elect_one()) {           // this k-block of the A operand is final: stream it to the record
+                            bulk_s2g(slot + (size_t)kb * 8192, sbase + k3ActHi + kb * 8192, 8192);
+                            bulk_s2g(slot + 65536 + (size_t)kb * 8192, sbase + k3ActLo + kb * 8192, 8192);
+                            if (layer == 6 && kb == 0) bulk_s2g(rec + kSlotV, sbase + k3EmbHi, 32768);
+                            bulk_commit();
+                        }
+                        __syncwarp();
+                    }
                     const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
                     { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
-                        const uint64_t ah = (is_act ? act_hi + (uint64_t)(ja * kStep) : emb_hi + (uint64_t)(j * kStep));
-                        const uint64_t al = (is_act ? act_lo + (uint64_t)(ja * kStep) : emb_lo + (uint64_t)(j * kStep));
-                        umma_f16(d, ah, bh, idesc256, j == 0 ? 0u : 1u);
-                        umma_f16(d, ah, bl, idesc256, 1u);
-                        umma_f16(d, al, bh, idesc256, 1u);
+                        if (is_act || j < n_emb) {
+                            const uint64_t ah = (is_act ? act_hi + (uint64_t)(ja * kStep) : emb_hi + (uint64_t)(j * kStep));
+                            const uint64_t al = (is_act ? act_lo + (uint64_t)(ja * kStep) : emb_lo + (uint64_t)(j * kStep));
+                            umma_f16(d, ah, bh, idesc256, j == 0 ? 0u : 1u);
+                            umma_f16(d, ah, bl, idesc256, 1u);
+                            umma_f16(d, al, bh, idesc256, 1u);
+                        } else {                              // bias block: encoding columns 48-63 (column 63 == 1.0) x [0 .. 0, bias]
+                            umma_f16(d, emb_hi + 3 * kStep, bh, idesc256, 1u);
+                            umma_f16(d, emb_hi + 3 * kStep, bl, idesc256, 1u);
+                        }
                         umma_commit(bar_empty + 8 * s);
-                        if (j + 1 == n_emb + n_act) umma_commit(bar_dfull + 8 * (layer & 1));
+                        if (j + 1 == nb) {
+                            if (kSave) bulk_wait_read0();     // the epilogue may overwrite the operand tiles once it sees this layer done
+                            umma_commit(bar_dfull + 8 * (layer & 1));
+                        }
                     }
                     __syncwarp();
                 }
@@ -213,7 +241,15 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 const uint32_t aph = (uint32_t)(tl * 9 + 8) & 1;
 #pragma unroll 1
                 for (int j = 0; j < 9; ++j, ++it) {
-                    if (j < 8) { PROF_T0(); mbar_wait(bar_aready + 8 * j, aph); PROF_ADD(pw_a); }
+                    if (j < 8) {
+                        { PROF_T0(); mbar_wait(bar_aready + 8 * j, aph); PROF_ADD(pw_a); }
+                        if (kSave && elect_one()) {
+                            bulk_s2g(rec + kSlotF + (size_t)j * 8192, sbase + k3ActHi + j * 8192, 8192);
+                            bulk_s2g(rec + kSlotF + 65536 + (size_t)j * 8192, sbase + k3ActLo + j * 8192, 8192);
+                            bulk_commit();
+                        }
+                        __syncwarp();
+                    }
                     const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
                     { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
                     tc_fence_after();
@@ -228,12 +264,25 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         umma_f16(d, ah + kStep, bl + kStep, idesc128, 1u);
                         umma_f16(d, al + kStep, bh + kStep, idesc128, 1u);
                         umma_commit(bar_empty + 8 * s);
-                        if (j == 8) umma_commit(bar_dfull + 8);
+                        if (j == 8) {
+                            if (kSave) bulk_wait_read0();
+                            umma_commit(bar_dfull + 8);
+                        }
                     }
                     __syncwarp();
                 }
             }
+            if (kSave) {      // views-layer output, staged in the (now free) activation tile by the last epilogue
+                mbar_wait(bar_hv, (uint32_t)tl & 1);
+                if (elect_one()) {
+                    bulk_s2g(rec + kSlotHV, sbase + k3ActHi, 32768);
+                    bulk_s2g(rec + kSlotHV + 32768, sbase + k3ActLo, 32768);
+                    bulk_commit();
+                }
+                __syncwarp();
+            }
         }
+        if (kSave) { if (elect_one()) bulk_wait0(); __syncwarp(); }
         if (g_prof3_on && lane == 0) {
             atomicAdd(&g_prof3[0], (unsigned long long)(clock64() - p_start));
             atomicAdd(&g_prof3[1], (unsigned long long)pw_a); atomicAdd(&g_prof3[2], (unsigned long long)pw_e);
@@ -247,19 +296,24 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint32_t ah = sbase + k3ActHi, al = sbase + k3ActLo, eh = sbase + k3EmbHi, el = sbase + k3EmbLo;
         long long pw_d = 0, p_start = g_prof3_on ? clock64() : 0;
         int tl = 0;
+        // point encoding of this thread's 16 columns (k-groups 2p, 2p+1); column 63 is the constant 1 that carries the biases
+        auto encode = [&](int tile, float* e16) {
+            const int gr = tile * (int)kRows + (int)row;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (gr < n_points) { x[0] = pts[3 * (size_t)gr]; x[1] = pts[3 * (size_t)gr + 1]; x[2] = pts[3 * (size_t)gr + 2]; }
+            if (p == 0)      { enc8<0>(x, 63, e16);  enc8<8>(x, 63, e16 + 8); }
+            else if (p == 1) { enc8<16>(x, 63, e16); enc8<24>(x, 63, e16 + 8); }
+            else if (p == 2) { enc8<32>(x, 63, e16); enc8<40>(x, 63, e16 + 8); }
+            else             { enc8<48>(x, 63, e16); enc8<56>(x, 63, e16 + 8); e16[15] = 1.f; }
+        };
+        float encv[16];
+        if ((int)blockIdx.x < num_tiles) encode(blockIdx.x, encv);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int grow = tile * (int)kRows + (int)row;
             const bool valid = grow < n_points;
-            uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
-            {   // point encoding: k-groups 2p, 2p+1 of the 64-wide tile
-                float x[3] = {0.f, 0.f, 0.f};
-                if (valid) { x[0] = pts[3 * (size_t)grow]; x[1] = pts[3 * (size_t)grow + 1]; x[2] = pts[3 * (size_t)grow + 2]; }
-                float v[8];
-                uint8_t* rh = rec + kSlotE;
-                if (p == 0)      { enc8<0>(x, 63, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 0, v); enc8<8>(x, 63, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 1, v); }
-                else if (p == 1) { enc8<16>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 2, v); enc8<24>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 3, v); }
-                else if (p == 2) { enc8<32>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 4, v); enc8<40>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 5, v); }
-                else             { enc8<48>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 6, v); enc8<56>(x, 63, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 7, v); }
+            {   // publish the (pre-computed) point encoding
+                emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p, encv);
+                emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p + 1, encv + 8);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_eready);
@@ -270,24 +324,22 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 { PROF_T0(); mbar_wait(bar_dfull + 8 * (layer & 1), (uint32_t)(tl * 5 + (layer >> 1)) & 1); PROF_ADD(pw_d); }
                 tc_fence_after();
                 if (layer == 5) {
-                    // every MMA of layer 5 (the last reader of the point encoding) is done: the tile now takes the
-                    // direction encoding, one k-group per column part; published by this layer's a_ready arrivals
+                    // every MMA of layer 5 (the last reader of the point encoding columns 0-31) is done: k-groups 0-3 now take
+                    // the direction encoding (column 31 = 1.0 for the bias); published by this layer's a_ready arrivals
                     float dvec[3] = {0.f, 0.f, 0.f};
                     if (valid) {
                         int ray = min(grow / n_samples, n_rays - 1);
                         dvec[0] = viewdirs[3 * (size_t)ray]; dvec[1] = viewdirs[3 * (size_t)ray + 1]; dvec[2] = viewdirs[3 * (size_t)ray + 2];
                     }
                     float v[8];
-                    uint8_t* rh = rec + kSlotV;
-                    if (p == 0)      { enc8<0>(dvec, 27, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 0, v); }
-                    else if (p == 1) { enc8<8>(dvec, 27, v);  emit_kgroup<kSave>(eh, el, rh, 16384, row, 1, v); }
-                    else if (p == 2) { enc8<16>(dvec, 27, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 2, v); }
-                    else             { enc8<24>(dvec, 27, v); emit_kgroup<kSave>(eh, el, rh, 16384, row, 3, v); }
+                    if (p == 0)      enc8<0>(dvec, 27, v);
+                    else if (p == 1) enc8<8>(dvec, 27, v);
+                    else if (p == 2) enc8<16>(dvec, 27, v);
+                    else             { enc8<24>(dvec, 27, v); v[7] = 1.f; }
+                    emit_kgroup<false>(eh, el, nullptr, 0, row, (uint32_t)p, v);
                 }
-                const float* bias = misc + kMiscBias + layer * 256;
                 const bool relu = layer != 8;
                 const uint32_t dcol = t_lane + (uint32_t)(layer & 1) * 256 + (uint32_t)p * 8;
-                uint8_t* slot = rec + (layer < 8 ? kSlotH0 + (size_t)layer * 131072 : kSlotF);
 #pragma unroll 1
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
                     float v[16];
@@ -298,8 +350,6 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     for (int u = 0; u < 2; ++u) {
                         const uint32_t c = (kb + u) * 32 + (uint32_t)p * 8;
                         float* w = v + 8 * u;
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-                        w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w; w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float t = relu ? fmaxf(w[j], 0.f) : fmaxf(w[j], -65504.f);
@@ -312,7 +362,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                             alpha_acc = fmaf(w[4], a1.x, alpha_acc); alpha_acc = fmaf(w[5], a1.y, alpha_acc);
                             alpha_acc = fmaf(w[6], a1.z, alpha_acc); alpha_acc = fmaf(w[7], a1.w, alpha_acc);
                         }
-                        emit_kgroup<kSave>(ah, al, slot, 65536, row, (kb + u) * 4 + (uint32_t)p, w);
+                        emit_kgroup<false>(ah, al, nullptr, 0, row, (kb + u) * 4 + (uint32_t)p, w);
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
@@ -321,10 +371,11 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 }
                 if (layer == 7) s_alpha[p * 128 + row] = alpha_acc;
             }
-            {   // views layer: ReLU, then rgb_linear as an fp32 dot product; 32 of the 128 columns per thread
+            // the next tile's encoding is computed while the tensor core works on the views layer
+            if (tile + (int)gridDim.x < num_tiles) encode(tile + (int)gridDim.x, encv);
+            {   // views layer: ReLU (bias already in the accumulator), then rgb_linear as an fp32 dot product; 32 of 128 columns per thread
                 { PROF_T0(); mbar_wait(bar_dfull + 8, (uint32_t)(tl * 5 + 4) & 1); PROF_ADD(pw_d); }
                 tc_fence_after();
-                const float* bias = misc + kMiscBias + 9 * 256;
                 const uint32_t c = (uint32_t)p * 32;
                 float v[32];
                 tmem_ld32(t_lane + 256 + c, v);
@@ -332,22 +383,18 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float hv = fmaxf(v[j] + __ldg(bias + c + j), 0.f);
+                    float hv = fmaxf(v[j], 0.f);
                     r0 = fmaf(hv, __ldg(misc + kMiscRgbW + c + j), r0);
                     r1 = fmaf(hv, __ldg(misc + kMiscRgbW + 128 + c + j), r1);
                     r2 = fmaf(hv, __ldg(misc + kMiscRgbW + 256 + c + j), r2);
                     v[j] = fminf(hv, 65504.f);
                 }
-                if (kSave) {
+                if (kSave) {      // stage hv in the activation tile (its last reader, this layer's MMAs, is done)
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_pack2(v[8 * k4 + 2 * i], v[8 * k4 + 2 * i + 1], h[i], l[i]);
-                        uint8_t* o = rec + kSlotHV + (size_t)((c >> 3) + k4) * 2048 + row * 16;
-                        st_global_v4_(o, h[0], h[1], h[2], h[3]);
-                        st_global_v4_(o + 32768, l[0], l[1], l[2], l[3]);
-                    }
+                    for (int k4 = 0; k4 < 4; ++k4) emit_kgroup<false>(ah, al, nullptr, 0, row, (c >> 3) + k4, v + 8 * k4);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_hv);
                 }
                 if (p > 0) { float* o = s_rgb + (p - 1) * 384; o[row] = r0; o[128 + row] = r1; o[256 + row] = r2; }
                 named_bar_sync(1, 512);

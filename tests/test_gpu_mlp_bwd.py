@@ -89,7 +89,8 @@ def test_activation_record(setup):
     acts, ref, n = setup["acts"], setup["ref"], setup["n"]
     assert acts.numel() == 3 * TILE
     E = decode(acts, TILE, SLOT_E, 8, 16384, n)
-    assert rel_err(E[:, :63], ref["e"]) < 2e-6 and float(E[:, 63].abs().max()) == 0.0
+    assert rel_err(E[:, :63], ref["e"]) < 2e-6
+    assert float((E[:, 63] - 1.0).abs().max()) == 0.0        # the constant column that carries the biases through the MMAs
     for l in range(8):
         H = decode(acts, TILE, SLOT_H0 + l * 131072, 32, 65536, n)
         assert rel_err(H, ref["post"][l]) < 5e-6, l
