@@ -25,6 +25,7 @@ SIGNATURES = {
     "cnerf_device_info": (_I, [POINTER(c_int), POINTER(c_int)]),
     "cnerf_pack_rays": (_I, [_P, _P, _I, _F, _F, _I, _I, _I, _I, _F, _P, _P]),
     "cnerf_image_rays": (_I, [_I, _I, POINTER(c_float), POINTER(c_float), _F, _F, _I, _I, _P, _P]),
+    "cnerf_gather_rays": (_I, [_I, _I, POINTER(c_float), POINTER(c_float), _P, _I, _F, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_stratified_z": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "cnerf_ray_points": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "cnerf_posenc": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
@@ -46,7 +47,6 @@ SIGNATURES = {
     "cnerf_mlp_bwd_heads": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P, _P]),
     "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
     "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
-    "cnerf_debug_profile": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -88,7 +88,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
-LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 5, "cnerf_mlp_bwd": 40, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 36, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 5, "cnerf_mlp_bwd": 16, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 12, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
 launch_count = 0
 # name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
 event_trace = {}

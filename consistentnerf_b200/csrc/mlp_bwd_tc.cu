@@ -30,9 +30,12 @@ constexpr size_t kGTileBytes = 65536 + 9 * 131072;     // 1 245 184 B
 
 // workspace map (bytes)
 constexpr size_t kWsAmax = 0;                                           // uint32: bits of max|d_raw|
-constexpr size_t kWsDwPart = 256;                                       // [148][128 x 512] fp32
-constexpr size_t kWsDbPart = kWsDwPart + (size_t)kNumSMs * 128 * 512 * 4;   // [148][2][256] fp32
-constexpr size_t kWsHeadPart = kWsDbPart + (size_t)kNumSMs * 2 * 256 * 4;   // [148][kHeadFloats] fp32
+constexpr int kDwPasses = 10;
+constexpr size_t kDwPassFloats = (size_t)kNumSMs * 128 * 512;           // one pass: [148][128 x 512] fp32
+constexpr size_t kDbPassFloats = (size_t)kNumSMs * 2 * 256;             // one pass: [148][2][256] fp32
+constexpr size_t kWsDwPart = 256;                                       // [10 passes][148][128 x 512] fp32
+constexpr size_t kWsDbPart = kWsDwPart + kDwPasses * kDwPassFloats * 4; // [10 passes][148][2][256] fp32
+constexpr size_t kWsHeadPart = kWsDbPart + kDwPasses * kDbPassFloats * 4;   // [148][kHeadFloats] fp32
 constexpr int kHeadFloats = 384 + 256 + 4;                              // dW_rgb, dW_alpha, db_rgb(3)+db_alpha
 constexpr size_t kWsBytes = kWsHeadPart + (size_t)kNumSMs * kHeadFloats * 4 + 256;
 
@@ -711,9 +714,12 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-// dst[(row0 + r) * ld + col0 + c] (+)= inv_scale * sum_cta part[cta][blk_off + r * blk_n + src_col0 + c]
-struct DwSeg { float* dst; int ld, row0, col0, ncols, blk_off, blk_n, src_col0; };
-struct DwSegs { int n; DwSeg s[6]; };
+// dst[(row0 + r) * ld + col0 + c] (+)= inv_scale * sum_cta part[pass][cta][blk_off + r * blk_n + src_col0 + c]
+// All passes write disjoint partial regions, so ONE launch reduces every segment of every pass (and one the biases).
+struct DwSeg { float* dst; int ld, row0, col0, ncols, blk_off, blk_n, src_col0, pass; };
+struct DwSegs { int n; DwSeg s[24]; };
+struct DbSeg { float* dst; int n, pass, src; };
+struct DbSegs { int n; DbSeg s[12]; };
 
 __global__ void dw_reduce_kernel(DwSegs S, const float* __restrict__ part, int n_cta, const uint32_t* __restrict__ amax_bits,
                                  int accumulate) {
@@ -721,7 +727,7 @@ __global__ void dw_reduce_kernel(DwSegs S, const float* __restrict__ part, int n
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128 * sg.ncols) return;
     int r = idx / sg.ncols, c = idx - r * sg.ncols;
-    const float* p = part + sg.blk_off + (size_t)r * sg.blk_n + sg.src_col0 + c;
+    const float* p = part + (size_t)sg.pass * kDwPassFloats + sg.blk_off + (size_t)r * sg.blk_n + sg.src_col0 + c;
     float acc = 0.f;
     for (int k = 0; k < n_cta; ++k) acc += p[(size_t)k * 128 * 512];
     acc *= 1.f / grad_scale(amax_bits);
@@ -729,14 +735,16 @@ __global__ void dw_reduce_kernel(DwSegs S, const float* __restrict__ part, int n
     *d = accumulate ? *d + acc : acc;
 }
 
-__global__ void db_reduce_kernel(float* __restrict__ dst, int n, const float* __restrict__ db_part, int src, int n_cta,
-                                 const uint32_t* __restrict__ amax_bits, int accumulate) {
+__global__ void db_reduce_kernel(DbSegs S, const float* __restrict__ db_part, int n_cta, const uint32_t* __restrict__ amax_bits,
+                                 int accumulate) {
+    const DbSeg sg = S.s[blockIdx.y];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    if (c >= sg.n) return;
+    const float* p = db_part + (size_t)sg.pass * kDbPassFloats + (size_t)sg.src * 256 + c;
     float acc = 0.f;
-    for (int k = 0; k < n_cta; ++k) acc += db_part[((size_t)k * 2 + src) * 256 + c];
+    for (int k = 0; k < n_cta; ++k) acc += p[(size_t)k * 512];
     acc *= 1.f / grad_scale(amax_bits);
-    dst[c] = accumulate ? dst[c] + acc : acc;
+    sg.dst[c] = accumulate ? sg.dst[c] + acc : acc;
 }
 
 // ------------------------------------------------------------------------------------
@@ -974,51 +982,50 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
     auto H = [](int l) { return (uint32_t)(kSlotH0 + (size_t)l * 131072); };
     const uint64_t a_rows = (uint64_t)tiles * (kTileBytes / 2048), g_rows = (uint64_t)tiles * (kGTileBytes / 2048);
     auto box_rows = [](const DwSrc& s) { return s.lo_off == s.kgroups * 2048 ? 2 * s.kgroups : s.kgroups; };
-    auto run_pass = [&](const DwPass& P, const DwSegs& S, float* db0, int n0, float* db1, int n1) -> int {
+    DwSegs all = {};
+    DbSegs alldb = {};
+    int pass = 0;
+    auto run_pass = [&](const DwPass& P, const DwSeg* segs, int nseg, float* db0, int n0, float* db1, int n1) -> int {
         CUtensorMap ma, mx0, mx1;
         int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]));
         if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]));
         if (r == CNERF_OK) r = make_record_map(&mx1, c.a, a_rows, box_rows(P.x[P.n_x - 1]));
         if (r != CNERF_OK) return r;
-        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(ma, mx0, mx1, P, tiles, c.dw_part, c.db_part);
+        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(ma, mx0, mx1, P, tiles, c.dw_part + (size_t)pass * kDwPassFloats,
+                                                                 c.db_part + (size_t)pass * kDbPassFloats);
         CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
-        int maxc = 0;
-        for (int i = 0; i < S.n; ++i) maxc = S.s[i].ncols > maxc ? S.s[i].ncols : maxc;
-        dw_reduce_kernel<<<dim3(ceil_div(128 * maxc, 256), S.n), 256, 0, st>>>(S, c.dw_part, grid, c.amax, accumulate);
-        CNERF_LAUNCH_CHECK("dw_reduce_kernel");
-        if (db0) { db_reduce_kernel<<<ceil_div(n0, 256), 256, 0, st>>>(db0, n0, c.db_part, 0, grid, c.amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
-        if (db1) { db_reduce_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(db1, n1, c.db_part, 1, grid, c.amax, accumulate); CNERF_LAUNCH_CHECK("db_reduce_kernel"); }
+        for (int i = 0; i < nseg; ++i) { all.s[all.n] = segs[i]; all.s[all.n].pass = pass; ++all.n; }
+        if (db0) alldb.s[alldb.n++] = {db0, n0, pass, 0};
+        if (db1) alldb.s[alldb.n++] = {db1, n1, pass, 1};
+        ++pass;
         return CNERF_OK;
     };
     {   // encoding pass: dW0 = G0^T E, dW5[:, :63] = G5^T E
         DwPass P = {}; P.n_a = 2; P.n_x = 1; P.db_mask = 3;
         P.a[0] = {(uint32_t)g_slot(0), 32, 65536}; P.a[1] = {(uint32_t)g_slot(5), 32, 65536}; P.x[0] = {(uint32_t)kSlotE, 8, 16384};
-        DwSegs S = {}; S.n = 4;
-        S.s[0] = {d_pts_w[0], 63, 0, 0, 63, 0 * 128 * 64, 64, 0};
-        S.s[1] = {d_pts_w[0], 63, 128, 0, 63, 1 * 128 * 64, 64, 0};
-        S.s[2] = {d_pts_w[5], 319, 0, 0, 63, 2 * 128 * 64, 64, 0};
-        S.s[3] = {d_pts_w[5], 319, 128, 0, 63, 3 * 128 * 64, 64, 0};
-        if ((rc = run_pass(P, S, d_pts_b[0], 256, d_pts_b[5], 256)) != CNERF_OK) return rc;
+        DwSeg S[4] = {{d_pts_w[0], 63, 0, 0, 63, 0 * 128 * 64, 64, 0, 0}, {d_pts_w[0], 63, 128, 0, 63, 1 * 128 * 64, 64, 0, 0},
+                      {d_pts_w[5], 319, 0, 0, 63, 2 * 128 * 64, 64, 0, 0}, {d_pts_w[5], 319, 128, 0, 63, 3 * 128 * 64, 64, 0, 0}};
+        if ((rc = run_pass(P, S, 4, d_pts_b[0], 256, d_pts_b[5], 256)) != CNERF_OK) return rc;
     }
     for (int l = 1; l <= 8; ++l) {   // 256-wide hidden inputs: layers 1..7 (layer 5: the h4 columns) and feature_linear (l == 8)
         DwPass P = {}; P.n_a = 1; P.n_x = 1; P.db_mask = (l == 5) ? 0 : 1;
         P.a[0] = {(uint32_t)g_slot(l), 32, 65536}; P.x[0] = {H(l - 1), 32, 65536};
         float* dst = l == 8 ? d_feature_w : d_pts_w[l];
         const int ld = l == 5 ? 319 : 256, c0 = l == 5 ? 63 : 0;
-        DwSegs S = {}; S.n = 2;
-        S.s[0] = {dst, ld, 0, c0, 256, 0, 256, 0};
-        S.s[1] = {dst, ld, 128, c0, 256, 128 * 256, 256, 0};
+        DwSeg S[2] = {{dst, ld, 0, c0, 256, 0, 256, 0, 0}, {dst, ld, 128, c0, 256, 128 * 256, 256, 0, 0}};
         float* db = l == 5 ? nullptr : (l == 8 ? d_feature_b : d_pts_b[l]);
-        if ((rc = run_pass(P, S, db, 256, nullptr, 0)) != CNERF_OK) return rc;
+        if ((rc = run_pass(P, S, 2, db, 256, nullptr, 0)) != CNERF_OK) return rc;
     }
     {   // views_linears.0: X = [feature (256), direction encoding (27 of 32)]
         DwPass P = {}; P.n_a = 1; P.n_x = 2; P.db_mask = 1;
         P.a[0] = {(uint32_t)g_slot(9), 16, 32768}; P.x[0] = {(uint32_t)kSlotF, 32, 65536}; P.x[1] = {(uint32_t)kSlotV, 4, 16384};
-        DwSegs S = {}; S.n = 2;
-        S.s[0] = {d_views_w, 283, 0, 0, 256, 0, 256, 0};
-        S.s[1] = {d_views_w, 283, 0, 256, 27, 128 * 256, 32, 0};
-        if ((rc = run_pass(P, S, d_views_b, 128, nullptr, 0)) != CNERF_OK) return rc;
+        DwSeg S[2] = {{d_views_w, 283, 0, 0, 256, 0, 256, 0, 0}, {d_views_w, 283, 0, 256, 27, 128 * 256, 32, 0, 0}};
+        if ((rc = run_pass(P, S, 2, d_views_b, 128, nullptr, 0)) != CNERF_OK) return rc;
     }
+    dw_reduce_kernel<<<dim3(ceil_div(128 * 256, 256), all.n), 256, 0, st>>>(all, c.dw_part, grid, c.amax, accumulate);
+    CNERF_LAUNCH_CHECK("dw_reduce_kernel");
+    db_reduce_kernel<<<dim3(1, alldb.n), 256, 0, st>>>(alldb, c.db_part, grid, c.amax, accumulate);
+    CNERF_LAUNCH_CHECK("db_reduce_kernel");
     return CNERF_OK;
 }
 

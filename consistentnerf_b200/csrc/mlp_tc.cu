@@ -35,8 +35,7 @@ namespace cnerf {
 struct BlkInfo {
     uint8_t layer, half, a_src, a_kg;           // a_src: 0 = encoding buffer, 1 = activation buffer
     uint8_t first, last_of_layer, wait_a, kvalid;
-    uint16_t src_k0;
-    uint8_t wait_a1, flags;                     // pipelined kernel: see build_program (flags: 1 = release A k-blocks 0-3, 2 = half done)
+    uint16_t src_k0, pad;
 };
 __constant__ BlkInfo c_blocks[kMaxBlocks];
 __constant__ int c_num_blocks;
@@ -60,13 +59,6 @@ static std::vector<BlkInfo> build_program() {
                 b.layer = (uint8_t)layer; b.half = (uint8_t)h; b.a_src = kbs[j].src; b.a_kg = kbs[j].kg;
                 b.first = j == 0; b.last_of_layer = (h == halves - 1) && (j + 1 == kbs.size());
                 b.wait_a = (h == 0 && j == 0); b.kvalid = kbs[j].kvalid; b.src_k0 = kbs[j].k0;
-                // Pipelined kernel (mlp_fused2_kernel): activation k-blocks 0-3 are produced by epilogue group A, 4-7 by
-                // group B.  wait_a / wait_a1: first block that needs group A's / group B's output (or the D half they
-                // drain); flag 1: last read of activation k-blocks 0-3 in this layer (group A may overwrite them);
-                // flag 2: last block of this N-half (its accumulator is complete).
-                b.wait_a1 = (h == 0) && (layer == 0 ? j == 0 : (kbs[j].src == 1 && kbs[j].kg == 16));
-                bool rel = (h == 1) && (layer == 0 ? j == 0 : (kbs[j].src == 1 && kbs[j].kg == 12));
-                b.flags = (uint8_t)((rel ? 1 : 0) | ((j + 1 == kbs.size()) ? 2 : 0));
                 prog.push_back(b);
             }
     }
@@ -356,325 +348,6 @@ mlp_fused_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ 
 
 
 // ------------------------------------------------------------------------------------
-// Pipelined fused kernel: activations live in TENSOR MEMORY between layers.
-//
-//   TMEM columns   [0,256)   fp32 accumulator, two 128-column N-halves
-//                  [256,384) A operand hi (fp16 pairs: column 256 + k/2),  [384,512) A operand lo
-//   SMEM           point/direction encoding tile (SS-mode k-blocks), an 11-stage weight ring, scalars
-//
-// 16 epilogue warps: warp e owns TMEM lanes 32*(e&3).. and accumulator columns 64*(e>>2)..  Group A (columns
-// 0-127) drains N-half 0 while the tensor core works on N-half 1 and writes the next layer's A k-blocks 0-3 in
-// place as soon as the MMAs have consumed the old ones (bar_afree); group B (columns 128-255) drains N-half 1
-// while the next layer's N-half 0 already runs on k-blocks 0-3.  tcgen05.mma reads A from TMEM (TS mode), so
-// shared-memory bandwidth carries only the weights, and the training-mode activation record is written with
-// coalesced 16-byte global stores straight from the epilogue registers.
-// ------------------------------------------------------------------------------------
-// Optional in-kernel phase profile (cycles summed over CTAs): enabled by cnerf_debug_profile(1, ...).
-//  [0] MMA lane total  [1] wait A group 0  [2] wait A group 1  [3] wait weights  [4] loader wait empty
-//  [8] group A total   [9] wait D  [10] wait a_free      [12] group B total  [13] wait D
-__device__ unsigned long long g_prof[16];
-__device__ int g_prof_on;
-#define PROF_T0() long long pt0__ = g_prof_on ? clock64() : 0
-#define PROF_ADD(var) do { if (g_prof_on) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
-
-constexpr int kThreads2 = 576;                           // 16 epilogue warps + loader warp + MMA warp
-constexpr uint32_t k2EmbHi = 0, k2EmbLo = 16384;         // 8 k-groups each
-constexpr uint32_t k2SAlpha = 32768;                     // float[4][128]
-constexpr uint32_t k2SRgb = 34816;                       // float[3][128]
-constexpr uint32_t k2Ring = 36864;
-constexpr int k2Stages = 11;
-constexpr uint32_t k2Bars = k2Ring + k2Stages * kBlockBytes;   // 217088
-constexpr uint32_t k2TmemSlot = k2Bars + 256;
-constexpr uint32_t k2Smem = k2Bars + 512;
-constexpr uint32_t kTmAHi = 256, kTmALo = 384;
-
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// 8 fp32 -> hi/lo words; optionally to the SMEM operand tile and / or the global record (k-group kg, row)
-__device__ __forceinline__ void split8(const float* v, uint32_t* h, uint32_t* l) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-}
-template <bool kSave>
-__device__ __forceinline__ void emit_enc8(uint32_t hi_base, uint32_t lo_base, uint8_t* rec_hi, size_t lo_off, uint32_t row,
-                                          uint32_t kg, const float* v) {
-    uint32_t h[4], l[4];
-    split8(v, h, l);
-    uint32_t off = kg * kLBO + row * 16;
-    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
-    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
-    if (kSave) {
-        st_global_v4(rec_hi + off, h[0], h[1], h[2], h[3]);
-        st_global_v4(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
-    }
-}
-
-template <bool kSave>
-__global__ void __launch_bounds__(kThreads2, 1)
-mlp_fused2_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
-                  const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
-                  uint8_t* __restrict__ acts) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + k2Bars, bar_empty = bar_full + 8 * k2Stages;
-    const uint32_t bar_dfull = bar_empty + 8 * k2Stages;       // [2]  accumulator half complete
-    const uint32_t bar_aready = bar_dfull + 16;                 // [2]  epilogue group done (A columns written, D half drained)
-    const uint32_t bar_afree = bar_aready + 16;                 //      A k-blocks 0-3 of the current layer consumed
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k2TmemSlot);
-    float* s_alpha = reinterpret_cast<float*>(smem + k2SAlpha);
-    float* s_rgb = reinterpret_cast<float*>(smem + k2SRgb);
-    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
-    const int nblk = c_num_blocks;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < k2Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_dfull, 1); mbar_init(bar_dfull + 8, 1);
-        mbar_init(bar_aready, 256); mbar_init(bar_aready + 8, 256);
-        mbar_init(bar_afree, 1);
-        fence_barrier_init();
-    }
-    if (warp == 17) tmem_alloc(sbase + k2TmemSlot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 16) {
-        // ===== weight loader =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            long long pw_empty = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int b = 0; b < nblk; ++b, ++it) {
-                    uint32_t s = it % k2Stages, ph = (it / k2Stages) & 1;
-                    { PROF_T0(); mbar_wait(bar_empty + 8 * s, ph ^ 1); PROF_ADD(pw_empty); }
-                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
-                    bulk_g2s(sbase + k2Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
-                }
-            if (g_prof_on) atomicAdd(&g_prof[4], (unsigned long long)pw_empty);
-        }
-    } else if (warp == 17) {
-        // ===== MMA issuer =====
-        // The whole warp walks the (static) block program so that control flow stays warp-uniform; one elected lane
-        // issues.  Descriptors are base + offset adds on precomputed 64-bit values: the issue loop must stay well
-        // under the 64 cycles one M=128 x N=128 x K=16 MMA takes (measured: 70 cycles/MMA with a lean loop, 100-150
-        // with per-instruction descriptor construction or a divergent single-lane loop).
-        constexpr uint32_t idesc = instr_desc(128, 128);
-        const uint64_t bdesc0 = smem_desc(sbase + k2Ring);                    // + stage * (16384 >> 4), lo half + 512
-        const uint64_t edesc_hi = smem_desc(sbase + k2EmbHi), edesc_lo = smem_desc(sbase + k2EmbLo);
-        const uint32_t ta_hi0 = tmem + kTmAHi, ta_lo0 = tmem + kTmALo;
-        uint32_t it = 0, a0_cnt = 0, a1_cnt = 0;
-        long long pw_a0 = 0, pw_a1 = 0, pw_full = 0, p_start = g_prof_on ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-#pragma unroll 1
-            for (int layer = 0; layer < kNumLayers; ++layer) {
-                const int halves = layer == 9 ? 1 : 2;
-                const int n_emb_first = (layer == 0 || layer == 5) ? 2 : 0, n_act = layer == 0 ? 0 : 8, n_emb_last = layer == 9 ? 1 : 0;
-                const int nb = n_emb_first + n_act + n_emb_last;
-#pragma unroll 1
-                for (int h = 0; h < halves; ++h) {
-                    const uint32_t d = tmem + (uint32_t)h * 128;
-#pragma unroll 1
-                    for (int j = 0; j < nb; ++j, ++it) {
-                        const bool is_act = j >= n_emb_first && j < n_emb_first + n_act;
-                        const int kb = is_act ? j - n_emb_first : (j < n_emb_first ? j : 0);      // k-block within its source
-                        if (h == 0 && j == 0) { PROF_T0(); mbar_wait(bar_aready, a0_cnt & 1); ++a0_cnt; PROF_ADD(pw_a0); }
-                        if (h == 0 && (layer == 0 ? j == 0 : (is_act && kb == 4))) { PROF_T0(); mbar_wait(bar_aready + 8, a1_cnt & 1); ++a1_cnt; PROF_ADD(pw_a1); }
-                        const uint32_t s = it % k2Stages, ph = (it / k2Stages) & 1;
-                        { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t bh = bdesc0 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
-                            const uint32_t acc0 = j == 0 ? 0u : 1u;
-                            if (!is_act) {                                    // encoding tile in shared memory (SS)
-                                const uint64_t ah = edesc_hi + (uint64_t)(kb * 4 * (kLBO >> 4)), al = edesc_lo + (uint64_t)(kb * 4 * (kLBO >> 4));
-                                umma_f16(d, ah, bh, idesc, acc0);
-                                umma_f16(d, ah, bl, idesc, 1u);
-                                umma_f16(d, al, bh, idesc, 1u);
-                                umma_f16(d, ah + 2 * (kLBO >> 4), bh + 2 * (kLBO >> 4), idesc, 1u);
-                                umma_f16(d, ah + 2 * (kLBO >> 4), bl + 2 * (kLBO >> 4), idesc, 1u);
-                                umma_f16(d, al + 2 * (kLBO >> 4), bh + 2 * (kLBO >> 4), idesc, 1u);
-                            } else {                                          // activations in tensor memory (TS)
-                                const uint32_t ah = ta_hi0 + (uint32_t)kb * 16, al = ta_lo0 + (uint32_t)kb * 16;
-                                umma_f16_ts(d, ah, bh, idesc, acc0);
-                                umma_f16_ts(d, ah, bl, idesc, 1u);
-                                umma_f16_ts(d, al, bh, idesc, 1u);
-                                umma_f16_ts(d, ah + 8, bh + 2 * (kLBO >> 4), idesc, 1u);
-                                umma_f16_ts(d, ah + 8, bl + 2 * (kLBO >> 4), idesc, 1u);
-                                umma_f16_ts(d, al + 8, bh + 2 * (kLBO >> 4), idesc, 1u);
-                            }
-                            umma_commit(bar_empty + 8 * s);
-                            // group A may overwrite A k-blocks 0-3 once N-half 1 has consumed them
-                            if (h == 1 && (layer == 0 ? j == 0 : (is_act && kb == 3))) umma_commit(bar_afree);
-                            if (j + 1 == nb) umma_commit(bar_dfull + 8 * h);
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-        if (g_prof_on && lane == 0) {
-            atomicAdd(&g_prof[0], (unsigned long long)(clock64() - p_start));
-            atomicAdd(&g_prof[1], (unsigned long long)pw_a0); atomicAdd(&g_prof[2], (unsigned long long)pw_a1);
-            atomicAdd(&g_prof[3], (unsigned long long)pw_full);
-        }
-    } else {
-        // ===== prologue + epilogue warps =====
-        const int q = warp & 3, p = warp >> 2, g = p >> 1;            // lane quarter, column quarter, group
-        const uint32_t row = (uint32_t)(q * 32 + lane);
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-        const uint32_t bar_d = bar_dfull + 8 * g, bar_a = bar_aready + 8 * g;
-        int tl = 0;                                                   // tiles done by this CTA
-        long long pw_d = 0, pw_free = 0, p_start = g_prof_on ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            const int grow = tile * (int)kRows + (int)row;
-            const bool valid = grow < n_points;
-            uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
-            // the previous tile's last layer still reads the direction encoding: group A saw it finish in its own
-            // layer-9 epilogue, group B waits for the same phase here
-            if (tl > 0 && g == 1) mbar_wait(bar_dfull, (uint32_t)((tl - 1) * 10 + 9) & 1);
-            {   // point encoding: 16 of the 64 columns per thread
-                float x[3] = {0.f, 0.f, 0.f};
-                if (valid) { x[0] = pts[3 * (size_t)grow]; x[1] = pts[3 * (size_t)grow + 1]; x[2] = pts[3 * (size_t)grow + 2]; }
-                float v[8];
-                const uint32_t eh = sbase + k2EmbHi, el = sbase + k2EmbLo;
-                uint8_t* rh = rec + kSlotE;
-                if (p == 0)      { enc_group8<0>(x, 63, v);  emit_enc8<kSave>(eh, el, rh, 16384, row, 0, v); enc_group8<8>(x, 63, v);  emit_enc8<kSave>(eh, el, rh, 16384, row, 1, v); }
-                else if (p == 1) { enc_group8<16>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 2, v); enc_group8<24>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 3, v); }
-                else if (p == 2) { enc_group8<32>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 4, v); enc_group8<40>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 5, v); }
-                else             { enc_group8<48>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 6, v); enc_group8<56>(x, 63, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 7, v); }
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-            }
-            float alpha_acc = 0.f;
-#pragma unroll 1
-            for (int layer = 0; layer < 9; ++layer) {
-                { PROF_T0(); mbar_wait(bar_d, (uint32_t)(tl * (g ? 9 : 10) + layer) & 1); PROF_ADD(pw_d); }
-                tc_fence_after();
-                const float* bias = misc + kMiscBias + layer * 256;
-                const bool relu = layer != 8;
-                uint8_t* slot = rec + (layer < 8 ? kSlotH0 + (size_t)layer * 131072 : kSlotF);
-#pragma unroll 1
-                for (uint32_t ch = 0; ch < 2; ++ch) {
-                    const uint32_t c = (uint32_t)p * 64 + ch * 32;
-                    float v[32];
-                    tmem_ld32(t_lane + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c + j));
-                        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = relu ? fmaxf(v[j], 0.f) : fmaxf(v[j], -65504.f);
-                        v[j] = fminf(t, 65504.f);
-                    }
-                    if (layer == 7) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 aw = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + j));
-                            alpha_acc = fmaf(v[j], aw.x, alpha_acc); alpha_acc = fmaf(v[j + 1], aw.y, alpha_acc);
-                            alpha_acc = fmaf(v[j + 2], aw.z, alpha_acc); alpha_acc = fmaf(v[j + 3], aw.w, alpha_acc);
-                        }
-                    }
-                    uint32_t h[16], l[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-                    if (g == 0 && ch == 0) {      // the other N-half must be done with the old A k-blocks 0-3
-                        PROF_T0(); mbar_wait(bar_afree, (uint32_t)(tl * 9 + layer) & 1); PROF_ADD(pw_free);
-                        tc_fence_after();
-                    }
-                    tmem_st16(t_lane + kTmAHi + (c >> 1), h);
-                    tmem_st16(t_lane + kTmALo + (c >> 1), l);
-                    if (kSave) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            uint8_t* o = slot + (size_t)((c >> 3) + k4) * 2048 + row * 16;
-                            st_global_v4(o, h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
-                            st_global_v4(o + 65536, l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]);
-                        }
-                    }
-                }
-                if (layer == 5 && g == 1) {
-                    // all of layer 5 is done (it read the point encoding): the buffer now takes the direction encoding
-                    float dvec[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        int ray = min(grow / n_samples, n_rays - 1);
-                        dvec[0] = viewdirs[3 * (size_t)ray]; dvec[1] = viewdirs[3 * (size_t)ray + 1]; dvec[2] = viewdirs[3 * (size_t)ray + 2];
-                    }
-                    float v[8];
-                    const uint32_t eh = sbase + k2EmbHi, el = sbase + k2EmbLo;
-                    uint8_t* rh = rec + kSlotV;
-                    if (p == 2) { enc_group8<0>(dvec, 27, v);  emit_enc8<kSave>(eh, el, rh, 16384, row, 0, v); enc_group8<8>(dvec, 27, v);  emit_enc8<kSave>(eh, el, rh, 16384, row, 1, v); }
-                    else        { enc_group8<16>(dvec, 27, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 2, v); enc_group8<24>(dvec, 27, v); emit_enc8<kSave>(eh, el, rh, 16384, row, 3, v); }
-                    fence_proxy_async();
-                }
-                if (layer == 7) s_alpha[p * 128 + row] = alpha_acc;
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-            }
-            if (g == 0) {
-                // views layer (N = 128, accumulator half 0): ReLU, then rgb_linear as an fp32 dot product
-                mbar_wait(bar_dfull, (uint32_t)(tl * 10 + 9) & 1);
-                tc_fence_after();
-                const float* bias = misc + kMiscBias + 9 * 256;
-                float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
-                for (uint32_t ch = 0; ch < 2; ++ch) {
-                    const uint32_t c = (uint32_t)p * 64 + ch * 32;
-                    float v[32];
-                    tmem_ld32(t_lane + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float hv = fmaxf(v[j] + __ldg(bias + c + j), 0.f);
-                        r0 = fmaf(hv, __ldg(misc + kMiscRgbW + c + j), r0);
-                        r1 = fmaf(hv, __ldg(misc + kMiscRgbW + 128 + c + j), r1);
-                        r2 = fmaf(hv, __ldg(misc + kMiscRgbW + 256 + c + j), r2);
-                        if (kSave) v[j] = fminf(hv, 65504.f);
-                    }
-                    if (kSave) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            uint32_t h[4], l[4];
-                            split8(v + 8 * k4, h, l);
-                            uint8_t* o = rec + kSlotHV + (size_t)((c >> 3) + k4) * 2048 + row * 16;
-                            st_global_v4(o, h[0], h[1], h[2], h[3]);
-                            st_global_v4(o + 32768, l[0], l[1], l[2], l[3]);
-                        }
-                    }
-                }
-                if (p == 1) { s_rgb[row] = r0; s_rgb[128 + row] = r1; s_rgb[256 + row] = r2; }
-                named_bar_sync(1, 256);
-                if (p == 0 && valid) {
-                    float4 o;
-                    o.x = r0 + s_rgb[row] + __ldg(misc + kMiscRgbB);
-                    o.y = r1 + s_rgb[128 + row] + __ldg(misc + kMiscRgbB + 1);
-                    o.z = r2 + s_rgb[256 + row] + __ldg(misc + kMiscRgbB + 2);
-                    o.w = s_alpha[row] + s_alpha[128 + row] + s_alpha[256 + row] + s_alpha[384 + row] + __ldg(misc + kMiscAlphaB);
-                    *reinterpret_cast<float4*>(raw + 4 * (size_t)grow) = o;
-                }
-                named_bar_sync(1, 256);          // s_rgb is reused by the next tile
-                tc_fence_before();
-            }
-        }
-        if (g_prof_on && lane == 0 && (warp == 0 || warp == 8)) {
-            const int o = warp == 0 ? 8 : 12;
-            atomicAdd(&g_prof[o], (unsigned long long)(clock64() - p_start));
-            atomicAdd(&g_prof[o + 1], (unsigned long long)pw_d); atomicAdd(&g_prof[o + 2], (unsigned long long)pw_free);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 17) tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------
 // unit self-test of descriptors / layout / TMEM mapping:  d[128,n] = a[128,k] b[n,k]^T
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
@@ -962,13 +635,12 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     static bool use_v1 = false;
     static int impl = 3;
     if (!attr_set) {
-        const char* ev = getenv("CNERF_MLP_IMPL");          // 1: serial SS kernel, 2: TMEM-resident N=128 halves, 3 (default): N=256
-        if (ev && ev[0] >= '1' && ev[0] <= '3') impl = ev[0] - '0';
+        const char* ev = getenv("CNERF_MLP_IMPL");          // 1: first-generation serial kernel (kept for A/B runs), default 3: mlp_fwd3.cu
+        if (ev && ev[0] == '1') impl = 1;
         use_v1 = impl == 1;
         cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused_kernel)");
         attr_set = true;
     }
@@ -977,16 +649,6 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
     if (impl == 3)
         return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
-    if (!use_v1) {
-        if (acts)
-            mlp_fused2_kernel<true><<<grid, kThreads2, k2Smem, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
-                                                                                  n_samples, n_rays, raw, (uint8_t*)acts);
-        else
-            mlp_fused2_kernel<false><<<grid, kThreads2, k2Smem, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
-                                                                                   n_samples, n_rays, raw, nullptr);
-        CNERF_LAUNCH_CHECK("mlp_fused2_kernel");
-        return CNERF_OK;
-    }
     if (acts)
         mlp_fused_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,
                                                                                 n_samples, n_rays, raw, (uint8_t*)acts);
@@ -1031,17 +693,6 @@ extern "C" int cnerf_umma_selftest_ts(const float* a, const float* b, int n, int
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_selftest_ts_kernel)");
     umma_selftest_ts_kernel<<<1, 128, smem, as_stream(stream)>>>(a, b, n, k, d);
     CNERF_LAUNCH_CHECK("umma_selftest_ts_kernel");
-    return CNERF_OK;
-}
-
-// Debug: switch the in-kernel phase profile of the pipelined kernel on/off and read (then clear) its 16 counters.
-extern "C" int cnerf_debug_profile(int enable, unsigned long long* out16) {
-    unsigned long long zero[16] = {0};
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_prof, sizeof(zero));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof_on, &enable, sizeof(int));
-    if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile");
     return CNERF_OK;
 }
 

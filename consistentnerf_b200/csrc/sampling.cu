@@ -70,6 +70,38 @@ __global__ void image_rays_kernel(int H, int W, Mat3 K, Mat34 c2w, float near_, 
     write_ray(rays + (size_t)i * (use_viewdirs ? 11 : 8), o, d, near_, far_, use_viewdirs, vd);
 }
 
+// Batch sampler back end (train(): NP/run_nerf_view.py:1443-1517, NP/run_nerf.py:718-760): rays of SELECTED pixels of one
+// view generated from the pose, plus the gathers of the target colour / prior depth / consistency mask at the same
+// pixels -- one launch instead of a full-image get_rays, three host->device image copies and five fancy-index gathers.
+__global__ void gather_rays_kernel(int H, int W, Mat3 K, Mat34 c2w, const int32_t* __restrict__ pix, int n, float near_,
+                                   float far_, int use_viewdirs, int ndc, const float* __restrict__ img,
+                                   const float* __restrict__ depth, const float* __restrict__ mask, float* __restrict__ rays,
+                                   float* __restrict__ target, float* __restrict__ depth_out, float* __restrict__ mask_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pid = pix[i];
+    const int py = pid / W, px = pid - py * W;
+    float dx = __fdiv_rn(__fsub_rn((float)px, K.m[2]), K.m[0]);
+    float dy = -__fdiv_rn(__fsub_rn((float)py, K.m[5]), K.m[4]);
+    float dz = -1.f;
+    float d[3], o[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w.m[4 * r]), __fmul_rn(dy, c2w.m[4 * r + 1])), __fmul_rn(dz, c2w.m[4 * r + 2]));
+        o[r] = c2w.m[4 * r + 3];
+    }
+    float vd[3] = {0.f, 0.f, 0.f};
+    if (use_viewdirs) unit_dir(d, vd);
+    if (ndc) ndc_transform((float)H, (float)W, K.m[0], 1.f, o, d);
+    write_ray(rays + (size_t)i * (use_viewdirs ? 11 : 8), o, d, near_, far_, use_viewdirs, vd);
+    if (target && img) {
+        target[3 * (size_t)i] = __ldg(img + 3 * (size_t)pid); target[3 * (size_t)i + 1] = __ldg(img + 3 * (size_t)pid + 1);
+        target[3 * (size_t)i + 2] = __ldg(img + 3 * (size_t)pid + 2);
+    }
+    if (depth_out && depth) depth_out[i] = __ldg(depth + pid);
+    if (mask_out && mask) mask_out[i] = __ldg(mask + pid);
+}
+
 // ------------------------------------------------------------------------------------
 // K1 stratified z  (NP/run_nerf.py:360-384)
 // ------------------------------------------------------------------------------------
@@ -320,6 +352,21 @@ extern "C" int cnerf_image_rays(int H, int W, const float* K_host, const float* 
     for (int i = 0; i < 12; ++i) P.m[i] = c2w_host[i];
     image_rays_kernel<<<ceil_div(H * W, 256), 256, 0, as_stream(stream)>>>(H, W, K, P, near_, far_, use_viewdirs, ndc, rays);
     CNERF_LAUNCH_CHECK("image_rays_kernel");
+    return CNERF_OK;
+}
+
+extern "C" int cnerf_gather_rays(int H, int W, const float* K_host, const float* c2w_host, const int32_t* pix, int n,
+                                 float near_, float far_, int use_viewdirs, int ndc, const float* img, const float* depth,
+                                 const float* mask, float* rays, float* target, float* depth_out, float* mask_out, void* stream) {
+    CNERF_REQUIRE(H > 0 && W > 0 && K_host && c2w_host && pix && rays && n >= 0, "cnerf_gather_rays: bad arguments");
+    CNERF_REQUIRE(!(target && !img) && !(depth_out && !depth) && !(mask_out && !mask), "cnerf_gather_rays: gather output without source");
+    if (n == 0) return CNERF_OK;
+    Mat3 K; Mat34 P;
+    for (int i = 0; i < 9; ++i) K.m[i] = K_host[i];
+    for (int i = 0; i < 12; ++i) P.m[i] = c2w_host[i];
+    gather_rays_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(H, W, K, P, pix, n, near_, far_, use_viewdirs, ndc, img, depth,
+                                                                        mask, rays, target, depth_out, mask_out);
+    CNERF_LAUNCH_CHECK("gather_rays_kernel");
     return CNERF_OK;
 }
 

@@ -21,7 +21,8 @@ import types
 
 import torch
 
-from . import consistency, nerf, render
+from . import consistency, nerf
+from .render import make_api        # (the package attribute `render` is the function, not the submodule)
 
 # names replaced in a reference script module, grouped by origin
 _RENDER_NAMES = ["batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays"]
@@ -39,7 +40,7 @@ def patch(module, with_depth=None):
     """Replace the hot-path globals of an imported reference script; returns the list of names patched."""
     if with_depth is None:
         with_depth = wants_depth(module)
-    api = render.make_api(with_depth)
+    api = make_api(with_depth)
     done = []
     for name in _RENDER_NAMES:
         if hasattr(module, name):

@@ -68,6 +68,25 @@ def image_rays(H: int, W: int, K, c2w, near: float, far: float, use_viewdirs: bo
     return out
 
 
+def gather_rays(H: int, W: int, K, c2w, pix: torch.Tensor, near: float, far: float, use_viewdirs: bool, ndc: bool,
+                img: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+    """Packed rays of the selected pixels of one view + gathers at the same pixels (batch sampler back end)."""
+    _need_cuda(pix, "gather_rays")
+    pix = pix.to(torch.int32).contiguous()
+    n, dev = pix.shape[0], pix.device
+    Kf = _lib.host_floats([K[i][j] for i in range(3) for j in range(3)])
+    c2w = c2w.detach().cpu() if isinstance(c2w, torch.Tensor) else c2w
+    Pf = _lib.host_floats([c2w[i][j] for i in range(3) for j in range(4)])
+    rays = torch.empty((n, 11 if use_viewdirs else 8), device=dev, dtype=_F32)
+    target = torch.empty((n, 3), device=dev, dtype=_F32) if img is not None else None
+    d_out = torch.empty(n, device=dev, dtype=_F32) if depth is not None else None
+    m_out = torch.empty(n, device=dev, dtype=_F32) if mask is not None else None
+    call("cnerf_gather_rays", int(H), int(W), Kf, Pf, ptr(pix), n, float(near), float(far), int(use_viewdirs), int(ndc),
+         ptr(_f32c(img)) if img is not None else None, ptr(_f32c(depth)) if depth is not None else None,
+         ptr(_f32c(mask)) if mask is not None else None, ptr(rays), ptr(target), ptr(d_out), ptr(m_out), stream())
+    return rays, target, d_out, m_out
+
+
 def stratified(rays: torch.Tensor, t_vals: torch.Tensor, t_rand: Optional[torch.Tensor], lindisp: bool):
     """K1: rays [n,8|11] -> z [n,S], pts [n,S,3]  (NP/run_nerf.py:360-384)."""
     _need_cuda(rays, "stratified")

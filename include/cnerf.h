@@ -55,6 +55,13 @@ int cnerf_pack_rays(const float* rays_o, const float* rays_d, int n, float near_
 int cnerf_image_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_,
                      int use_viewdirs, int ndc, float* rays, void* stream);
 
+/* Batch-sampler back end (train(): NP/run_nerf_view.py:1443-1517, NP/run_nerf.py:718-760): packed rays of the SELECTED pixels
+ * pix[n] (int32 row-major pixel ids, device) of one view, and the gathers of target colour img [H,W,3], prior depth [H,W]
+ * and mask [H,W] (device fp32, any may be NULL together with its output) at the same pixels. */
+int cnerf_gather_rays(int H, int W, const float* K_host, const float* c2w_host, const int32_t* pix, int n, float near_,
+                      float far_, int use_viewdirs, int ndc, const float* img, const float* depth, const float* mask,
+                      float* rays, float* target, float* depth_out, float* mask_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1 stratified sampling -- render_rays NP/run_nerf.py:354-384.
  * ---------------------------------------------------------------------------------------- */
@@ -221,9 +228,8 @@ int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* ma
                          float divisor, float coef, float n_ref, int use_unmasked, const float* out,
                          const float* g_loss, float* d_pred, void* stream);
 
-/* Debug aid: enable/disable the in-kernel phase profile of the fused MLP kernel and read + clear its 16 cycle
- * counters (host pointer, may be NULL).  Synchronises the device. */
-int cnerf_debug_profile(int enable, unsigned long long* out16);
+/* Debug aid: enable/disable the in-kernel phase profile of the fused forward kernel (mlp_fwd3.cu) and read + clear its
+ * 16 cycle counters (host pointer, may be NULL).  Synchronises the device. */
 int cnerf_debug_profile3(int enable, unsigned long long* out16);
 /* Debug aid: measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */
 int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream);

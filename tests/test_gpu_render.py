@@ -165,3 +165,57 @@ def test_whole_image_render_from_pose(cn):
     ref = O.render_rays(rays, pc, pf, ARCH, n_samples=64, n_importance=128, white_bkgd=True)
     assert_close(rgb.reshape(-1, 3), ref["rgb_map"], 1e-4, 1e-5)
     assert_close(depth.reshape(-1), ref["depth_map"], 1e-4, 1e-5)
+
+
+def test_ray_bank_batches_match_reference_sampling(cn):
+    """The device batch sampler yields exactly what train() builds per step (NP/run_nerf_view.py:1443-1517): rays through
+    the chosen pixels of the chosen view and the targets / prior depths / masks gathered at those pixels."""
+    V, H, W = 3, 12, 20
+    gen = torch.Generator().manual_seed(7)
+    images = torch.rand(V, H, W, 3, generator=gen)
+    depths = 2 + torch.rand(V, H, W, generator=gen)
+    masks = (torch.rand(V, H, W, generator=gen) > 0.5).float()
+    K = np.array([[30.0, 0, W / 2], [0, 30.0, H / 2], [0, 0, 1]], dtype=np.float32)
+    poses = torch.eye(4)[None].repeat(V, 1, 1)
+    poses[:, :3, 3] = torch.randn(V, 3, generator=gen)
+    poses[1, :3, :3] = torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    bank = cn.RayBank(images.numpy(), poses.numpy(), K, near=2.0, far=6.0, use_viewdirs=True, depths=depths.numpy(),
+                      masks=masks.numpy(), seed=3)
+    for kw in (dict(n_rand=64), dict(n_rand=50, patches=2, patch_size=4), dict(n_rand=30, precrop_frac=0.5, view=1)):
+        b = bank.sample(**kw)
+        v, pix = b["view"], b["pix"].cpu().long()
+        n = kw["n_rand"] + kw.get("patches", 0) * kw.get("patch_size", 16) ** 2
+        assert pix.shape[0] == n and b["rays"].shape == (n, 11)
+        rand_part = pix[-kw["n_rand"]:]
+        assert rand_part.unique().numel() == kw["n_rand"]                     # replace=False
+        if "precrop_frac" in kw:
+            yy, xx = rand_part // W, rand_part % W
+            assert yy.min() >= H // 2 - 3 and yy.max() <= H // 2 + 2 and xx.min() >= W // 2 - 5 and xx.max() <= W // 2 + 4
+        ro, rd = O.pixel_rays(H, W, K, poses[v, :3, :4])
+        ref = O.pack_rays(ro.reshape(-1, 3)[pix], rd.reshape(-1, 3)[pix], 2.0, 6.0, True)
+        assert_close(b["rays"], ref, 1e-6, 1e-7)
+        assert torch.equal(b["target"].cpu(), images[v].reshape(-1, 3)[pix])
+        assert torch.equal(b["depth"].cpu(), depths[v].reshape(-1)[pix])
+        assert torch.equal(b["mask"].cpu(), masks[v].reshape(-1)[pix])
+        assert torch.equal(b["batch_rays"][1], b["rays"][:, 3:6])
+
+
+def test_render_path_matches_per_image_render(cn):
+    H = W = 16
+    K = np.array([[20.0, 0, 8.0], [0, 20.0, 8.0], [0, 0, 1]], dtype=np.float32)
+    poses = []
+    for k in range(3):
+        c2w = torch.eye(4)
+        c2w[:3, 3] = torch.tensor([0.1 * k, -0.1, 4.0])
+        poses.append(c2w)
+    pc = O.make_params(4, sigma_bias=0.5, **ARCH)
+    pf = O.make_params(5, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    kw = _kwargs(cn, coarse, fine)
+    rgbs, disps, accs = cn.render_path(torch.stack(poses).to(DEV), (H, W, 20.0), K, 4096, kw)
+    assert rgbs.shape == (3, H, W, 3) and disps.shape == (3, H, W) and accs.shape == (3, H, W)
+    with torch.no_grad():
+        for k in range(3):
+            rgb, disp, acc, depth, _ = cn.render(H, W, K, chunk=4096, c2w=poses[k][:3, :4].to(DEV), **kw)
+            assert np.array_equal(rgbs[k], rgb.cpu().numpy()) and np.array_equal(accs[k], acc.cpu().numpy())
+            np.testing.assert_array_equal(disps[k], disp.cpu().numpy())
