@@ -47,8 +47,12 @@ SIGNATURES = {
     "cnerf_mlp_bwd_heads": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P, _P]),
     "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
     "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_profile4": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_umma_selftest_pair": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_debug_pair_layout": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_debug_umma_rate_pair": (_I, [_I, _I, _I, _P, _P, _P]),
     "cnerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cnerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_sample_pdf": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -88,7 +92,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
-LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 5, "cnerf_mlp_bwd": 16, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 12, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 6, "cnerf_mlp_bwd": 16, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 12, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
 launch_count = 0
 # name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
 event_trace = {}

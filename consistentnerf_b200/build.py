@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libcnerf.so")
-SOURCES = ["api.cu", "sampling.cu", "composite.cu", "crossview.cu", "linear_simt.cu", "mlp_tc.cu", "mlp_bwd_tc.cu", "mlp_fwd3.cu"]
+SOURCES = ["api.cu", "sampling.cu", "composite.cu", "crossview.cu", "linear_simt.cu", "mlp_tc.cu", "mlp_bwd_tc.cu", "mlp_fwd3.cu", "mlp_fwd4.cu", "pair_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -53,7 +53,7 @@ def _compile(src: str, verbose: bool) -> str:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile if sources changed (content hash), return the path of libcnerf.so."""
     os.makedirs(OBJ, exist_ok=True)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "mlp_layout.cuh"),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "mlp_layout.cuh"), os.path.join(CSRC, "mlp_blocks.cuh"),
                                                        os.path.join(PKG, "..", "include", "cnerf.h")]
     stamp = os.path.join(OBJ, "stamp")
     digest = _digest(deps)

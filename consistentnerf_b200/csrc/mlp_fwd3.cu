@@ -13,12 +13,13 @@
 // layer L+1 on k-block 0 while the epilogue is still converting k-blocks 1..7 -- it writes the OTHER accumulator, so
 // the only serialisation left is the first k-block.  The training variant writes the activation record with
 // coalesced 16-byte global stores straight from the epilogue registers.
-#include "mlp_layout.cuh"
+#include "mlp_blocks.cuh"
 
 namespace cnerf {
 
 __device__ unsigned long long g_prof3[16];
 __device__ int g_prof3_on;
+__device__ int g_dbg3;          // timing experiments only (results become wrong): 1 skip tcgen05.ld, 2 skip operand stores, 4 skip proxy fences
 #define PROF_T0() long long pt0__ = g_prof3_on ? clock64() : 0
 #define PROF_ADD(var) do { if (g_prof3_on) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
 
@@ -32,34 +33,6 @@ constexpr int k3Stages = 4;
 constexpr uint32_t k3Bars = k3Ring + k3Stages * kBlockBytes;      // 229376
 constexpr uint32_t k3TmemSlot = k3Bars + 192;
 constexpr uint32_t k3Smem = k3Bars + 256;
-constexpr int k3NumBlocks = 4 + 17 * 4 + 20 + 17 * 3 + 9;         // 152 (one bias block for every layer without an encoding block)
-
-// ------------------------------------------------------------------------------------
-// weight stream: blocks in consumption order
-//   layers 0-8: [256 rows x 16 k] blocks, element (n, k) at (k/8)*4096 + n*16 + (k%8)*2 (hi), +8192 (lo)
-//   layer 9   : [128 rows x 32 k] blocks, element (n, k) at (k/8)*2048 + n*16 + (k%8)*2 (hi), +8192 (lo)
-// Biases ride on the tensor core: the padding column of the encoding tile (column 63 of the point encoding, column 31
-// of the direction encoding) holds 1.0 and the matching weight column holds the bias.  Layers whose input has no
-// encoding part get one extra block that multiplies encoding columns 48-63 with [0 ... 0, bias].
-// ------------------------------------------------------------------------------------
-struct Blk3 { int layer, src_k0, kvalid, bias_k; };       // bias_k: column of the block that carries the bias (-1: none)
-
-__device__ __forceinline__ Blk3 block3_info(int b) {
-    // layer 0: 4 blocks; 1-4: 16 + bias; 5: 4 + 16; 6-8: 16 + bias; 9: 8 + 1
-    if (b < 4) return {0, 16 * b, b == 3 ? 15 : 16, b == 3 ? 15 : -1};
-    b -= 4;
-    if (b < 68) { int l = 1 + b / 17, j = b % 17; return j < 16 ? Blk3{l, 16 * j, 16, -1} : Blk3{l, 0, 0, 15}; }
-    b -= 68;
-    if (b < 4) return {5, 16 * b, b == 3 ? 15 : 16, b == 3 ? 15 : -1};
-    b -= 4;
-    if (b < 16) return {5, 63 + 16 * b, 16, -1};
-    b -= 16;
-    if (b < 51) { int l = 6 + b / 17, j = b % 17; return j < 16 ? Blk3{l, 16 * j, 16, -1} : Blk3{l, 0, 0, 15}; }
-    b -= 51;
-    if (b < 8) return {9, 32 * b, 32, -1};
-    return {9, 256, 27, 31};
-}
-
 __global__ void __launch_bounds__(256)
 pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
     const Blk3 bi = block3_info(blockIdx.x);
@@ -82,49 +55,6 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
         *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(dst + kBlockHalfBytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }
-}
-
-// ------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_global_v4_(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-// 8 fp32 of one k-group -> hi/lo words into the SMEM operand tile and (training) the global record
-template <bool kSave>
-__device__ __forceinline__ void emit_kgroup(uint32_t hi_base, uint32_t lo_base, uint8_t* rec_hi, size_t lo_off, uint32_t row,
-                                            uint32_t kg, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    const uint32_t off = kg * kLBO + row * 16;
-    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
-    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
-    if (kSave) {
-        st_global_v4_(rec_hi + off, h[0], h[1], h[2], h[3]);
-        st_global_v4_(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
-    }
-}
-
-template <int J>
-__device__ __forceinline__ float enc_col3(const float (&x)[3], int width) {
-    if (J >= width) return 0.f;
-    if (J < 3) return x[J];
-    constexpr int b = (J - 3) / 3, c = (J - 3) % 3, oct = b / 2;
-    float arg = x[c] * (float)(1 << oct);
-    return (b & 1) ? cosf(arg) : sinf(arg);
-}
-template <int J0>
-__device__ __forceinline__ void enc8(const float (&x)[3], int width, float* v) {
-    v[0] = enc_col3<J0 + 0>(x, width); v[1] = enc_col3<J0 + 1>(x, width); v[2] = enc_col3<J0 + 2>(x, width);
-    v[3] = enc_col3<J0 + 3>(x, width); v[4] = enc_col3<J0 + 4>(x, width); v[5] = enc_col3<J0 + 5>(x, width);
-    v[6] = enc_col3<J0 + 6>(x, width); v[7] = enc_col3<J0 + 7>(x, width);
 }
 
 // ------------------------------------------------------------------------------------
@@ -183,7 +113,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint64_t emb_hi = smem_desc(sbase + k3EmbHi), emb_lo = smem_desc(sbase + k3EmbLo);
         constexpr uint32_t kStep = 2 * (kLBO >> 4);                               // two k-groups = one K=16 step of the A tile
         uint32_t it = 0;
-        long long pw_a = 0, pw_full = 0, pw_e = 0, p_start = g_prof3_on ? clock64() : 0;
+        long long pw_a = 0, pw_full = 0, pw_e = 0, pw_issue = 0, p_start = g_prof3_on ? clock64() : 0;
         int tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
@@ -215,6 +145,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
                     { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
                     tc_fence_after();
+                    PROF_T0();
                     if (elect_one()) {
                         const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
                         if (is_act || j < n_emb) {
@@ -234,6 +165,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         }
                     }
                     __syncwarp();
+                    PROF_ADD(pw_issue);
                 }
             }
             {   // views layer: N = 128, [128 x 32] blocks, accumulator D[1] columns 256..383
@@ -287,6 +219,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             atomicAdd(&g_prof3[0], (unsigned long long)(clock64() - p_start));
             atomicAdd(&g_prof3[1], (unsigned long long)pw_a); atomicAdd(&g_prof3[2], (unsigned long long)pw_e);
             atomicAdd(&g_prof3[3], (unsigned long long)pw_full);
+            atomicAdd(&g_prof3[4], (unsigned long long)pw_issue);
         }
     } else {
         // ===== prologue + epilogue warps: thread = (row, p); per k-block of 32 columns it owns columns 8p..8p+7 =====
@@ -295,6 +228,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t ah = sbase + k3ActHi, al = sbase + k3ActLo, eh = sbase + k3EmbHi, el = sbase + k3EmbLo;
         long long pw_d = 0, p_start = g_prof3_on ? clock64() : 0;
+        const int dbg = g_dbg3;
         int tl = 0;
         // point encoding of this thread's 16 columns (k-groups 2p, 2p+1); column 63 is the constant 1 that carries the biases
         auto encode = [&](int tile, float* e16) {
@@ -343,9 +277,14 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 #pragma unroll 1
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
                     float v[16];
-                    tmem_ld8(dcol + kb * 32, v);
-                    tmem_ld8(dcol + kb * 32 + 32, v + 8);
-                    tmem_ld_wait();
+                    if (!(dbg & 1)) {
+                        tmem_ld8(dcol + kb * 32, v);
+                        tmem_ld8(dcol + kb * 32 + 32, v + 8);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = (float)(j + lane) * 0.01f;
+                    }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const uint32_t c = (kb + u) * 32 + (uint32_t)p * 8;
@@ -362,8 +301,8 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                             alpha_acc = fmaf(w[4], a1.x, alpha_acc); alpha_acc = fmaf(w[5], a1.y, alpha_acc);
                             alpha_acc = fmaf(w[6], a1.z, alpha_acc); alpha_acc = fmaf(w[7], a1.w, alpha_acc);
                         }
-                        emit_kgroup<false>(ah, al, nullptr, 0, row, (kb + u) * 4 + (uint32_t)p, w);
-                        fence_proxy_async();
+                        if (!(dbg & 2)) emit_kgroup<false>(ah, al, nullptr, 0, row, (kb + u) * 4 + (uint32_t)p, w);
+                        if (!(dbg & 4)) fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
@@ -447,14 +386,17 @@ int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, c
 }  // namespace cnerf
 
 // Debug: in-kernel phase profile of mlp_fused3_kernel (cycles summed over CTAs):
-//  [0] MMA warp total  [1] wait A k-blocks  [2] wait encoding  [3] wait weights   [8] epilogue total  [9] wait D
+//  [0] MMA warp total  [1] wait A k-blocks  [2] wait encoding  [3] wait weights  [4] MMA issue + commit  [8] epilogue total  [9] wait D
+// enable: bit 0 = profile on, bits 1.. = g_dbg3 timing experiments
 extern "C" int cnerf_debug_profile3(int enable, unsigned long long* out16) {
     using namespace cnerf;
     unsigned long long zero[16] = {0};
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_prof3, sizeof(zero));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3, zero, sizeof(zero));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3_on, &enable, sizeof(int));
+    const int on = enable & 1, dbg = enable >> 1;
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3_on, &on, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_dbg3, &dbg, sizeof(int));
     if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile3");
     return CNERF_OK;
 }

@@ -60,6 +60,7 @@ struct cnerf_weights {
     uint8_t* stream_bwd = nullptr;  // transposed blocks in the order the data-gradient chain consumes them
     uint8_t* stream_bwd3 = nullptr; // chain stream of the N=256 backward kernel: [256 x 16] transposed blocks
     uint8_t* stream3 = nullptr;     // forward stream of the N=256 kernel (mlp_fwd3.cu): [256 x 16] blocks
+    uint8_t* stream4 = nullptr;     // forward stream of the CTA-pair kernel (mlp_fwd4.cu): per block two 8 KB halves
     float* misc = nullptr;          // biases + alpha/rgb heads (fp32)
     int num_blocks = 0, num_blocks_bwd = 0;
     int device = -1;

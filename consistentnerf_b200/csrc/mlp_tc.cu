@@ -554,6 +554,10 @@ int bwd_stream3_blocks();
 int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st);
 int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st);                                // mlp_fwd3.cu
 int stream3_blocks();
+int pack_stream4(const RawParams& p, uint8_t* stream4, cudaStream_t st);                                // mlp_fwd4.cu
+size_t stream4_bytes();
+int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, const float* viewdirs, int n_points,
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 }
@@ -581,8 +585,9 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
     if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd, (size_t)w->num_blocks_bwd * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->stream3, (size_t)stream3_blocks() * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd3, (size_t)bwd_stream3_blocks() * kBlockBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->stream4, stream4_bytes());
     if (e == cudaSuccess) e = cudaMalloc(&w->misc, kMiscFloats * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(w->stream); cudaFree(w->stream_bwd); cudaFree(w->stream3); cudaFree(w->stream_bwd3); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
+    if (e != cudaSuccess) { cudaFree(w->stream); cudaFree(w->stream_bwd); cudaFree(w->stream3); cudaFree(w->stream_bwd3); cudaFree(w->stream4); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
     *out = w;
     return CNERF_OK;
 }
@@ -593,6 +598,7 @@ extern "C" void cnerf_weights_destroy(cnerf_weights* w) {
     cudaFree(w->stream_bwd);
     cudaFree(w->stream3);
     cudaFree(w->stream_bwd3);
+    cudaFree(w->stream4);
     cudaFree(w->misc);
     delete w;
 }
@@ -618,6 +624,7 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     int rc = pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
     if (rc == CNERF_OK) rc = pack_stream3(p, w->stream3, as_stream(stream));
     if (rc == CNERF_OK) rc = pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream));
+    if (rc == CNERF_OK) rc = pack_stream4(p, w->stream4, as_stream(stream));
     if (rc != CNERF_OK) return rc;
     w->packed = true;
     return CNERF_OK;
@@ -635,8 +642,10 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     static bool use_v1 = false;
     static int impl = 3;
     if (!attr_set) {
-        const char* ev = getenv("CNERF_MLP_IMPL");          // 1: first-generation serial kernel (kept for A/B runs), default 3: mlp_fwd3.cu
-        if (ev && ev[0] == '1') impl = 1;
+        // default 3: single-CTA N=256 kernel (mlp_fwd3.cu); kept for A/B runs: 4 = CTA-pair ping-pong kernel (mlp_fwd4.cu,
+        // correct but slower: measured in profiles/), 1 = first-generation serial kernel
+        const char* ev = getenv("CNERF_MLP_IMPL");
+        if (ev && (ev[0] == '1' || ev[0] == '4')) impl = ev[0] - '0';
         use_v1 = impl == 1;
         cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -647,6 +656,8 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     int n_points = (int)np64;
     int tiles = ceil_div(n_points, (int)kRows);
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    if (impl == 4)
+        return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     if (impl == 3)
         return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     if (acts)

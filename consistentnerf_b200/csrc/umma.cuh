@@ -170,4 +170,65 @@ __device__ __forceinline__ uint64_t smem_desc_any(uint32_t saddr, uint32_t lbo, 
 // instruction descriptor with both operands MN-major (transposed): bits 15 (a_major) and 16 (b_major)
 __host__ __device__ constexpr uint32_t instr_desc_mn(uint32_t M, uint32_t N) { return instr_desc(M, N) | (1u << 15) | (1u << 16); }
 
+// ------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of one cluster on the two SMs of a TPC issue ONE M=256 MMA; each CTA holds its own 128
+// rows of A and of D and HALF of B (N/2 rows), so the per-SM shared-memory traffic of the B operand halves.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {      // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// issued by the leader CTA (rank 0) only; descriptors are CTA-relative and resolved in both CTAs
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once the pair's previously issued MMAs are complete
+__device__ __forceinline__ void umma2_commit(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of any CTA of the cluster (address from mapa_u32); release at cluster scope publishes this thread's
+// earlier writes (after fence.proxy.async: also to the async proxy that feeds the peer-issued MMA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a LOCAL mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope); bounded like mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("cnerf: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 }  // namespace cnerf

@@ -599,8 +599,12 @@ class MaskedMSEFn(torch.autograd.Function):
 
 
 def umma_selftest(a: torch.Tensor, b: torch.Tensor, a_in_tmem: bool = False) -> torch.Tensor:
-    """d = a b^T through the tcgen05 building blocks (a [128,k], b [n,k]); A from SMEM or from tensor memory."""
+    """d = a b^T through the tcgen05 building blocks (a [128,k], b [n,k]); A from SMEM or from tensor memory.
+    a [256,k]: the CTA-pair (cta_group::2) variant."""
     a, b = _f32c(a), _f32c(b)
-    d = torch.empty((128, b.shape[0]), device=a.device, dtype=_F32)
+    d = torch.empty((a.shape[0], b.shape[0]), device=a.device, dtype=_F32)
+    if a.shape[0] == 256:
+        call("cnerf_umma_selftest_pair", ptr(a), ptr(b), b.shape[0], a.shape[1], ptr(d), stream())
+        return d
     call("cnerf_umma_selftest_ts" if a_in_tmem else "cnerf_umma_selftest", ptr(a), ptr(b), b.shape[0], a.shape[1], ptr(d), stream())
     return d

@@ -156,6 +156,9 @@ int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, floa
 int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream);
 /* Same product with the A operand staged in tensor memory (tcgen05.st + TS-mode MMA); k <= 256. */
 int cnerf_umma_selftest_ts(const float* a, const float* b, int n, int k, float* d, void* stream);
+/* CTA-pair variant (tcgen05 cta_group::2, one M=256 instruction stream for two SMs): d[256,n] = a[256,k] b[n,k]^T;
+ * each CTA of the pair holds its 128 rows of a/d and n/2 rows of b.  n%32==0, n<=256, k<=128. */
+int cnerf_umma_selftest_pair(const float* a, const float* b, int n, int k, float* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 alpha compositing -- raw2outputs NP/run_nerf.py:265-308 (depth_map as returned by
@@ -231,8 +234,17 @@ int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* ma
 /* Debug aid: enable/disable the in-kernel phase profile of the fused forward kernel (mlp_fwd3.cu) and read + clear its
  * 16 cycle counters (host pointer, may be NULL).  Synchronises the device. */
 int cnerf_debug_profile3(int enable, unsigned long long* out16);
+/* Same for the CTA-pair forward kernel (mlp_fwd4.cu). */
+int cnerf_debug_profile4(int enable, unsigned long long* out16);
 /* Debug aid: measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */
 int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream);
+/* Debug aid: cycles per N=256 K=16 SS tcgen05.mma, pair != 0: M=256 cta_group::2 on 74 CTA pairs, else M=128 on 148
+ * CTAs; traffic bit 0 adds concurrent st.shared traffic, bit 1 a bulk-copy ring fed from src (>= 1 MiB, device).
+ * out: 148 device floats. */
+/* Debug aid: TMEM data layout of an M=128 cta_group::2 accumulator (64 rows of a[128,k] per CTA, fp16 hi parts only):
+ * dump[2][128][256] = every CTA's TMEM window after d = a b^T. */
+int cnerf_debug_pair_layout(const float* a, const float* b, int n, int k, float* dump, void* stream);
+int cnerf_debug_umma_rate_pair(int pair, int iters, int traffic, const void* src, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,15 +11,17 @@ net = module_from_params(O.make_params(0, sigma_bias=0.5, **ARCH), ARCH)
 packed = net.packed_weights(); packed.refresh(dict(zip(net.spec.param_names(), [p.detach() for p in net.hot_params()])))
 n, S = 4096, 192
 pts = torch.randn(n, S, 3, device=dev); vd = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
-names = {0: "mma total", 1: "mma wait A kblocks", 2: "mma wait enc", 3: "mma wait weights", 8: "epilogue total", 9: "epilogue wait D"}
-for mode in ("infer", "train"):
+names = {0: "mma total", 1: "mma wait A kblocks", 2: "mma wait enc", 3: "mma wait weights", 4: "mma issue+commit", 8: "epilogue total", 9: "epilogue wait D"}
+IMPL = os.environ.get("CNERF_MLP_IMPL", "4")
+PROF = "cnerf_debug_profile3" if IMPL == "3" else "cnerf_debug_profile4"
+for mode, dbg in ([("infer", 0), ("infer", 1)] if IMPL == "4" else [("infer", 0), ("train", 0)]):
     fn = (lambda: cn.ops.fused_mlp_forward(packed, pts, vd)) if mode == "infer" else (lambda: cn.ops.fused_mlp_forward_train(packed, pts, vd))
     for _ in range(2): fn()
     out = (ctypes.c_ulonglong * 16)()
-    _lib.call("cnerf_debug_profile3", 1, out)
+    _lib.call(PROF, 1 | (dbg << 1), out)
     fn()
-    _lib.call("cnerf_debug_profile3", 0, out)
+    _lib.call(PROF, 0, out)
     tiles = n * S / 128 / 148
-    print(mode, "tiles/CTA %.1f" % tiles)
+    print("impl", IMPL, mode, "dbg", dbg, "128-point tiles per SM %.1f" % tiles)
     for k, nm in names.items():
         print(f"   {nm:20s} {out[k] / 148 / 1e3:10.1f} kcycles/CTA   {out[k] / 148 / tiles:10.0f} cycles/tile")

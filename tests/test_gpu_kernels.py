@@ -135,6 +135,16 @@ def test_umma_a_operand_in_tensor_memory(cn, n, k):
     assert rel_err(d, a.double() @ b.double().t()) < 2e-6
 
 
+@pytest.mark.parametrize("n,k", [(256, 16), (256, 128), (128, 64), (32, 32)])
+def test_umma_cta_pair(cn, n, k):
+    """One M=256 tcgen05.mma.cta_group::2 stream for two CTAs: each holds 128 rows of A/D and n/2 rows of B."""
+    gen = torch.Generator().manual_seed(n * 1000 + k + 2)
+    a = torch.randn(256, k, generator=gen)
+    b = torch.randn(n, k, generator=gen) * 0.1
+    d = cn.ops.umma_selftest(a.to(DEV), b.to(DEV))
+    assert rel_err(d, a.double() @ b.double().t()) < 2e-6
+
+
 @pytest.mark.parametrize("n_rays,n_samples", [(1, 1), (3, 64), (40, 192), (257, 33)])
 def test_fused_mlp_forward(cn, n_rays, n_samples):
     p = O.make_params(7, sigma_bias=0.3, **ARCH)
