@@ -61,6 +61,16 @@ __device__ __forceinline__ void emit_kgroup(uint32_t hi_base, uint32_t lo_base, 
     }
 }
 
+// 8 fp32 of one k-group -> hi/lo words straight into the global record
+__device__ __forceinline__ void emit_record(uint8_t* rec_hi, size_t lo_off, uint32_t row, uint32_t kg, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    const uint32_t off = kg * kLBO + row * 16;
+    st_global_v4_(rec_hi + off, h[0], h[1], h[2], h[3]);
+    st_global_v4_(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
+}
+
 template <int J>
 __device__ __forceinline__ float enc_col3(const float (&x)[3], int width) {
     if (J >= width) return 0.f;

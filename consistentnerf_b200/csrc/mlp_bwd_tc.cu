@@ -360,13 +360,14 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
     if (warp == 16) {
         // ===== weight loader =====
         if (lane == 0) {
+            const uint64_t keep = l2_policy_evict_last();
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
                 for (int b = 0; b < kC3NumBlocks; ++b, ++it) {
                     const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
-                    bulk_g2s(sbase + kC3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
+                    bulk_g2s_hint(sbase + kC3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s, keep);
                 }
         }
     } else if (warp == 17) {
@@ -375,6 +376,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         const uint64_t b256 = smem_desc_any(sbase + kC3Ring, 4096, 128);
         const uint64_t act_hi = smem_desc(sbase + kC3ActHi), act_lo = smem_desc(sbase + kC3ActLo);
         constexpr uint32_t kStep = 2 * (kLBO >> 4);
+        const uint64_t stream_pol = l2_policy_evict_first();
         uint32_t it = 0;
         int tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -383,8 +385,8 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
             auto store_kblock = [&](int layer, int kb) {
                 uint8_t* slot = grec + g_slot(layer);
                 const size_t lo_off = layer == 9 ? 32768 : 65536;
-                bulk_s2g(slot + (size_t)kb * 8192, sbase + kC3ActHi + kb * 8192, 8192);
-                bulk_s2g(slot + lo_off + (size_t)kb * 8192, sbase + kC3ActLo + kb * 8192, 8192);
+                bulk_s2g_hint(slot + (size_t)kb * 8192, sbase + kC3ActHi + kb * 8192, 8192, stream_pol);
+                bulk_s2g_hint(slot + lo_off + (size_t)kb * 8192, sbase + kC3ActLo + kb * 8192, 8192, stream_pol);
                 bulk_commit();
             };
 #pragma unroll 1

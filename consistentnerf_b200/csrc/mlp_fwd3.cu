@@ -20,8 +20,10 @@ namespace cnerf {
 __device__ unsigned long long g_prof3[16];
 __device__ int g_prof3_on;
 __device__ int g_dbg3;          // timing experiments only (results become wrong): 1 skip tcgen05.ld, 2 skip operand stores, 4 skip proxy fences
-#define PROF_T0() long long pt0__ = g_prof3_on ? clock64() : 0
-#define PROF_ADD(var) do { if (g_prof3_on) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
+// the phase profile is a separate template instantiation (kProf): every instruction in the MMA-issuing warp delays the tensor
+// pipe (tcgen05.mma issue is synchronous with execution, scripts/umma_rate.py), so the production kernels carry none of it
+#define PROF_T0() long long pt0__ = kProf ? clock64() : 0
+#define PROF_ADD(var) do { if (kProf) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
 
 constexpr int k3Threads = 576;                           // 16 epilogue warps + loader warp + MMA warp
 constexpr uint32_t k3ActHi = 0, k3ActLo = 65536;         // 32 k-groups x 2048 B each
@@ -60,7 +62,7 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
-template <bool kSave>
+template <bool kSave, bool kProf>
 __global__ void __launch_bounds__(k3Threads, 1)
 mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
@@ -95,13 +97,14 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     if (warp == 16) {
         // ===== weight loader =====
         if (lane == 0) {
+            const uint64_t keep = l2_policy_evict_last();
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
                 for (int b = 0; b < k3NumBlocks; ++b, ++it) {
                     const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
-                    bulk_g2s(sbase + k3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
+                    bulk_g2s_hint(sbase + k3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s, keep);
                 }
         }
     } else if (warp == 17) {
@@ -112,13 +115,14 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint64_t act_hi = smem_desc(sbase + k3ActHi), act_lo = smem_desc(sbase + k3ActLo);
         const uint64_t emb_hi = smem_desc(sbase + k3EmbHi), emb_lo = smem_desc(sbase + k3EmbLo);
         constexpr uint32_t kStep = 2 * (kLBO >> 4);                               // two k-groups = one K=16 step of the A tile
+        const uint64_t stream_pol = l2_policy_evict_first();
         uint32_t it = 0;
-        long long pw_a = 0, pw_full = 0, pw_e = 0, pw_issue = 0, p_start = g_prof3_on ? clock64() : 0;
+        long long pw_a = 0, pw_full = 0, pw_e = 0, pw_issue = 0, p_start = kProf ? clock64() : 0;
         int tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
             { PROF_T0(); mbar_wait(bar_eready, (uint32_t)tl & 1); PROF_ADD(pw_e); }
-            if (kSave && elect_one()) { bulk_s2g(rec + kSlotE, sbase + k3EmbHi, 32768); bulk_commit(); }
+            if (kSave && elect_one()) { bulk_s2g_hint(rec + kSlotE, sbase + k3EmbHi, 32768, stream_pol); bulk_commit(); }
             __syncwarp();
 #pragma unroll 1
             for (int layer = 0; layer < 9; ++layer) {
@@ -135,9 +139,9 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         const int kb = ja >> 1;
                         { PROF_T0(); mbar_wait(bar_aready + 8 * kb, aph); PROF_ADD(pw_a); }
                         if (kSave && elect_one()) {           // this k-block of the A operand is final: stream it to the record
-                            bulk_s2g(slot + (size_t)kb * 8192, sbase + k3ActHi + kb * 8192, 8192);
-                            bulk_s2g(slot + 65536 + (size_t)kb * 8192, sbase + k3ActLo + kb * 8192, 8192);
-                            if (layer == 6 && kb == 0) bulk_s2g(rec + kSlotV, sbase + k3EmbHi, 32768);
+                            bulk_s2g_hint(slot + (size_t)kb * 8192, sbase + k3ActHi + kb * 8192, 8192, stream_pol);
+                            bulk_s2g_hint(slot + 65536 + (size_t)kb * 8192, sbase + k3ActLo + kb * 8192, 8192, stream_pol);
+                            if (layer == 6 && kb == 0) bulk_s2g_hint(rec + kSlotV, sbase + k3EmbHi, 32768, stream_pol);
                             bulk_commit();
                         }
                         __syncwarp();
@@ -176,8 +180,8 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     if (j < 8) {
                         { PROF_T0(); mbar_wait(bar_aready + 8 * j, aph); PROF_ADD(pw_a); }
                         if (kSave && elect_one()) {
-                            bulk_s2g(rec + kSlotF + (size_t)j * 8192, sbase + k3ActHi + j * 8192, 8192);
-                            bulk_s2g(rec + kSlotF + 65536 + (size_t)j * 8192, sbase + k3ActLo + j * 8192, 8192);
+                            bulk_s2g_hint(rec + kSlotF + (size_t)j * 8192, sbase + k3ActHi + j * 8192, 8192, stream_pol);
+                            bulk_s2g_hint(rec + kSlotF + 65536 + (size_t)j * 8192, sbase + k3ActLo + j * 8192, 8192, stream_pol);
                             bulk_commit();
                         }
                         __syncwarp();
@@ -207,15 +211,15 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             if (kSave) {      // views-layer output, staged in the (now free) activation tile by the last epilogue
                 mbar_wait(bar_hv, (uint32_t)tl & 1);
                 if (elect_one()) {
-                    bulk_s2g(rec + kSlotHV, sbase + k3ActHi, 32768);
-                    bulk_s2g(rec + kSlotHV + 32768, sbase + k3ActLo, 32768);
+                    bulk_s2g_hint(rec + kSlotHV, sbase + k3ActHi, 32768, stream_pol);
+                    bulk_s2g_hint(rec + kSlotHV + 32768, sbase + k3ActLo, 32768, stream_pol);
                     bulk_commit();
                 }
                 __syncwarp();
             }
         }
         if (kSave) { if (elect_one()) bulk_wait0(); __syncwarp(); }
-        if (g_prof3_on && lane == 0) {
+        if (kProf && lane == 0) {
             atomicAdd(&g_prof3[0], (unsigned long long)(clock64() - p_start));
             atomicAdd(&g_prof3[1], (unsigned long long)pw_a); atomicAdd(&g_prof3[2], (unsigned long long)pw_e);
             atomicAdd(&g_prof3[3], (unsigned long long)pw_full);
@@ -227,8 +231,8 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint32_t row = (uint32_t)(q * 32 + lane);
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t ah = sbase + k3ActHi, al = sbase + k3ActLo, eh = sbase + k3EmbHi, el = sbase + k3EmbLo;
-        long long pw_d = 0, p_start = g_prof3_on ? clock64() : 0;
-        const int dbg = g_dbg3;
+        long long pw_d = 0, p_start = kProf ? clock64() : 0;
+        const int dbg = kProf ? g_dbg3 : 0;
         int tl = 0;
         // point encoding of this thread's 16 columns (k-groups 2p, 2p+1); column 63 is the constant 1 that carries the biases
         auto encode = [&](int tile, float* e16) {
@@ -349,7 +353,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 named_bar_sync(1, 512);      // the scratch aliases the encoding tile the next prologue rewrites
             }
         }
-        if (g_prof3_on && lane == 0 && warp == 0) {
+        if (kProf && lane == 0 && warp == 0) {
             atomicAdd(&g_prof3[8], (unsigned long long)(clock64() - p_start));
             atomicAdd(&g_prof3[9], (unsigned long long)pw_d);
         }
@@ -358,6 +362,8 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     __syncthreads();
     if (warp == 17) tmem_dealloc(tmem, 512);
 }
+
+static int g_prof3_host = 0;        // cnerf_debug_profile3: launch the instrumented instantiation
 
 int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st) {
     pack_weights3_kernel<<<k3NumBlocks, 256, 0, st>>>(p, stream3);
@@ -370,15 +376,22 @@ int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, c
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused3_kernel)");
         attr_set = true;
     }
     const int tiles = ceil_div(n_points, (int)kRows);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (acts) mlp_fused3_kernel<true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
-    else mlp_fused3_kernel<false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
+    if (g_prof3_host) {
+        if (acts) mlp_fused3_kernel<true, true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
+        else mlp_fused3_kernel<false, true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
+    } else {
+        if (acts) mlp_fused3_kernel<true, false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
+        else mlp_fused3_kernel<false, false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
+    }
     CNERF_LAUNCH_CHECK("mlp_fused3_kernel");
     return CNERF_OK;
 }
@@ -395,6 +408,7 @@ extern "C" int cnerf_debug_profile3(int enable, unsigned long long* out16) {
     if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_prof3, sizeof(zero));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3, zero, sizeof(zero));
     const int on = enable & 1, dbg = enable >> 1;
+    g_prof3_host = on;
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof3_on, &on, sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_dbg3, &dbg, sizeof(int));
     if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile3");

@@ -498,27 +498,39 @@ umma_bench_kernel(int mode, int n, int iters, int alt, float* __restrict__ out) 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *slot;
-    if (warp == 0) {
+    const uint32_t tmem0 = *slot;
+    if (warp == 0 || (warp == 1 && (alt & 128))) {
+        // alt & 128: two issuing warps, each with its own accumulator columns (and its own half of a 2n-row B tile)
+        const uint32_t tmem = tmem0 + (uint32_t)warp * 256;
         const uint32_t idesc = instr_desc(128, (uint32_t)n);
-        const uint32_t lbo_b = (uint32_t)n * 16;
+        const uint32_t lbo_b = (uint32_t)n * 16 * ((alt & 128) ? 2 : 1);
+        const uint32_t bar = sbase + 8192 + 16384 * 2 + 32 * (uint32_t)warp;
         uint64_t bd[4], ad[4];
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) {
-            bd[ks] = (uint64_t)(((b_s + ks * 2 * lbo_b) >> 4) & 0x3FFF) | ((uint64_t)(lbo_b >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
+            bd[ks] = (uint64_t)(((b_s + ((alt & 128) ? ks * 2048 + (uint32_t)warp * n * 16 : ks * 2 * lbo_b)) >> 4) & 0x3FFF) | ((uint64_t)(lbo_b >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
             ad[ks] = smem_desc(a_s + ks * 2 * kLBO);
         }
         const uint32_t d1 = (alt && n <= 128) ? tmem + 128 : tmem;
         // loop-structure variants (bits of `alt` above 1): 2 = mbarrier try_wait on a completed barrier per group of 4,
         // 4 = tcgen05.fence::after_thread_sync per group, 8 = tcgen05.commit per group, 16 = second commit per group
         const uint32_t bar2 = bar + 16, bar3 = bar + 24;
-        if (threadIdx.x == 0) { mbar_init(bar2, 1); mbar_init(bar3, 1); fence_barrier_init(); mbar_arrive(bar2); }
+        if ((threadIdx.x & 31) == 0) { if (warp == 1) mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); fence_barrier_init(); mbar_arrive(bar2); }
         __syncwarp();
         const bool ts = mode != 0;
         long long t0 = clock64();
+        uint32_t chain = threadIdx.x;
         for (int i = 0; i < iters; i += 4) {
             if (alt & 2) mbar_wait(bar2, 0);
             if (alt & 4) tc_fence_after();
+            if (alt & 32) {                    // ~60 dependent integer multiply-adds (a few hundred cycles of pure ALU latency)
+#pragma unroll
+                for (int r = 0; r < 60; ++r) chain = chain * 1664525u + 1013904223u + (uint32_t)i;
+            }
+            if (alt & 64) {                    // 8 loads of a shared-memory word that is not an mbarrier
+#pragma unroll
+                for (int r = 0; r < 8; ++r) chain += *reinterpret_cast<volatile uint32_t*>(smem + 8192 + 32768 + 40 + 4 * (chain & 1));
+            }
             if (elect_one()) {
                 if (!ts) {
                     umma_f16(tmem, ad[0], bd[0], idesc, 1u); umma_f16(d1, ad[1], bd[1], idesc, 1u);
@@ -536,11 +548,11 @@ umma_bench_kernel(int mode, int n, int iters, int alt, float* __restrict__ out) 
         __syncwarp();
         mbar_wait(bar, 0);
         long long t1 = clock64();
-        if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)iters;
+        if ((threadIdx.x & 31) == 0 && warp == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)iters + (chain == 0x12345u ? 1.f : 0.f);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem0, 512);
 }
 
 }  // namespace cnerf
@@ -710,7 +722,7 @@ extern "C" int cnerf_umma_selftest_ts(const float* a, const float* b, int n, int
 // Debug: cycles per tcgen05.mma (M=128, N=n, K=16) for `iters` back-to-back instructions on every SM; out[148] device floats.
 extern "C" int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream) {
     CNERF_REQUIRE(out && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0, "cnerf_debug_umma_rate: bad arguments");
-    size_t smem = 8192 + 32768 + 64;
+    size_t smem = 8192 + 32768 + 128;
     cudaError_t e = cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_bench_kernel)");
     umma_bench_kernel<<<kNumSMs, 128, smem, as_stream(stream)>>>(mode, n, iters, alt, out);
