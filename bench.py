@@ -42,12 +42,27 @@ KERNEL_FLOPS = {
     "cnerf_mlp_bwd_data": 2 * (128 * 256 + 8 * 256 * 256), # dX chain: views (128->256) + 8 x (256->256)
     "cnerf_mlp_bwd_weights": 2 * (593408 - 640),           # dW of the ten GEMM layers (all but the two narrow heads)
 }
+# algorithmic HBM bytes per point of the weight-gradient stage: its operands G_l and X_l (fp32-equivalent, 4 B per element, read
+# once): encoding pass G0+G5+E = 576 columns, eight 256x256 passes = 8 x 512, views pass G9+F+V = 416  
+DW_BYTES_PER_POINT = 4 * (576 + 8 * 512 + 416)
 KERNEL_NAMES = {
-    "cnerf_mlp_fwd": "mlp_fused_kernel<false> (K2+K3 forward, tcgen05)",
-    "cnerf_mlp_fwd_train": "mlp_fused_kernel<true> (K2+K3 forward + activation record, tcgen05)",
-    "cnerf_mlp_bwd_data": "mlp_bwd_data_kernel (K3b data-gradient chain, tcgen05)",
+    "cnerf_mlp_fwd": "mlp_fused3_kernel<false> (K2+K3 forward, tcgen05)",
+    "cnerf_mlp_fwd_train": "mlp_fused3_kernel<true> (K2+K3 forward + activation record, tcgen05)",
+    "cnerf_mlp_bwd_data": "mlp_bwd_data3_kernel (K3b data-gradient chain, tcgen05)",
     "cnerf_mlp_bwd_weights": "mlp_bwd_weight_kernel x10 passes + reductions (K3b weight gradients, tcgen05)",
 }
+# kernel symbol (as ncu names it) behind each traced call, for the DRAM traffic captured with `ncu --set full` (profiles/ncu_traffic.json)
+KERNEL_SYMBOL = {"cnerf_mlp_fwd": "mlp_fused3_kernel", "cnerf_mlp_fwd_train": "mlp_fused3_kernel",
+                 "cnerf_mlp_bwd_data": "mlp_bwd_data3_kernel", "cnerf_mlp_bwd_weights": "mlp_bwd_weight_kernel"}
+
+
+def ncu_traffic(call_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the call's kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))[KERNEL_SYMBOL[call_name]]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 NEAR, FAR, COEF = 2.0, 6.0, 0.2
 
 
@@ -108,6 +123,21 @@ class Clocks:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def roofline_of(top, kernels, kern_ms, tf_peak, hbm_peak, peak_src, step_tf):
+    """Roofline entry of the dominant traced kernel: the weight-gradient stage is HBM bound, the others tensor-pipe bound."""
+    k = kernels[top]
+    common = {"kernel": KERNEL_NAMES[top], "traffic": ncu_traffic(top), "peak_source": peak_src, "kernel_ms_per_step": kern_ms[top],
+              "mlp_step_tflops": step_tf, "mlp_step_tensor_frac": step_tf / tf_peak}
+    if top == "cnerf_mlp_bwd_weights":
+        return {**common, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["hbm_frac"],
+                "note": f"algorithmic operand bytes ({DW_BYTES_PER_POINT} B per point: G_l and X_l read once, fp32-equivalent) over the "
+                        f"step's {POINTS_PER_RAY * N_RAYS} points / time of the call (10 GEMM passes + reductions per network); the same "
+                        f"call reaches {k['achieved_tflops']:.0f} algorithmic TFLOP/s = {k['frac']:.3f} of the tensor roofline"}
+    return {**common, "bound": "tensor", "achieved": k["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": k["frac"],
+            "note": "algorithmic fp32-equivalent FLOPs of the GEMMs this call evaluates over the step's "
+                    f"{POINTS_PER_RAY * N_RAYS} points; every MAC is issued as 3 fp16 MMAs (hi*hi + hi*lo + lo*hi), so 1/3 is the ceiling"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -228,6 +258,12 @@ def run_b200(args):
                       "achieved_tflops": tf, "frac": tf / tf_peak}
     top = max(kern_ms, key=kern_ms.get)
     achieved = kernels[top]["achieved_tflops"]
+    if "cnerf_mlp_bwd_weights" in kernels:      # HBM-bound stage (ncu: 73 % DRAM throughput, 30 % tensor pipe): report both rooflines
+        k = kernels["cnerf_mlp_bwd_weights"]
+        gbs = DW_BYTES_PER_POINT * POINTS_PER_RAY * N_RAYS / (kern_ms["cnerf_mlp_bwd_weights"] * 1e-3) / 1e9
+        k["achieved_gbs"], k["hbm_frac"] = gbs, gbs / hbm_peak
+    mlp_flops_step = FLOP_PER_POINT * POINTS_PER_RAY * N_RAYS * (3 if train else 1)
+    step_tf = mlp_flops_step / (ms_step * 1e-3) / 1e12
     rays_per_s = N_RAYS * world / (ms_step * 1e-3)
     e2e_rays = N_RAYS * world / (ms_e2e * 1e-3)
     h2d = sum(x.numel() * x.element_size() for x in host[0])
@@ -248,11 +284,7 @@ def run_b200(args):
         "e2e": {"value": e2e_rays, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"kernel": KERNEL_NAMES[top], "bound": "tensor", "achieved": achieved,
-                     "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-                     "peak_source": peak_src, "kernel_ms_per_step": kern_ms[top],
-                     "note": "algorithmic fp32-equivalent FLOPs of the GEMMs this call evaluates over the step's "
-                             f"{POINTS_PER_RAY * N_RAYS} points; every MAC is issued as 3 fp16 MMAs (hi*hi + hi*lo + lo*hi)"},
+        "roofline": roofline_of(top, kernels, kern_ms, tf_peak, hbm_peak, peak_src, step_tf),
         "kernels": kernels,
         "cpu_baseline": cpu,
     }

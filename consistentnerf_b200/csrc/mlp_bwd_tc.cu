@@ -449,10 +449,14 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
             dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
             if (tl > 0) mbar_wait(bar_sdone, (uint32_t)(tl - 1) & 1);        // the previous tile's G0 has left the operand tile
             // G9 = (d_rgb W_rgb) * [hv > 0]: four k-blocks of 32 columns
-#pragma unroll 1
+            uint4 mhv[4];                                                     // ReLU masks of the views layer: all four loads in flight at once
+#pragma unroll
+            for (uint32_t kb = 0; kb < 4; ++kb)
+                mhv[kb] = __ldg(reinterpret_cast<const uint4*>(arec + kSlotHV + (size_t)(kb * 4 + (uint32_t)p) * 2048 + row * 16));
+#pragma unroll
             for (uint32_t kb = 0; kb < 4; ++kb) {
                 const uint32_t kg = kb * 4 + (uint32_t)p, c = kg * 8;
-                const uint4 m = __ldg(reinterpret_cast<const uint4*>(arec + kSlotHV + (size_t)kg * 2048 + row * 16));
+                const uint4 m = mhv[kb];
                 const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
                 float v[8];
 #pragma unroll
@@ -471,18 +475,23 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
 #pragma unroll 1
             for (int step = 0; step < 9; ++step) {
                 const int L = 9 - step;                           // D = gradient w.r.t. the input of layer L = G_{L-1} before masking
+                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;      // hi half of h_{L-1} (L <= 8)
+                // the ReLU masks do not depend on this step's MMAs: all eight loads are issued BEFORE waiting for the accumulator,
+                // so their HBM latency (the record is not L2 resident) hides behind the tensor-core work of the step
+                uint4 mk[8];
+                if (L != 9) {
+#pragma unroll
+                    for (uint32_t kb = 0; kb < 8; ++kb)
+                        mk[kb] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(kb * 4 + p) * 2048 + row * 16));
+                }
                 mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1);
                 tc_fence_after();
-                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;      // hi half of h_{L-1} (L <= 8)
                 const uint32_t dcol = t_lane + (uint32_t)(step & 1) * 256 + (uint32_t)p * 8;
-#pragma unroll 1
+#pragma unroll
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
                     float v[16];
                     uint4 m[2];
-                    if (L != 9) {
-                        m[0] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(kb * 4 + p) * 2048 + row * 16));
-                        m[1] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)((kb + 1) * 4 + p) * 2048 + row * 16));
-                    }
+                    if (L != 9) { m[0] = mk[kb]; m[1] = mk[kb + 1]; }
                     tmem_ld8g(dcol + kb * 32, v);
                     tmem_ld8g(dcol + kb * 32 + 32, v + 8);
                     tmem_ld_wait();
@@ -939,7 +948,7 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
-    static int impl = 0;
+    static int impl = 0;      // same selection as cnerf_weights_refresh (mlp_tc.cu: bwd_impl), which packs only the stream in use
     if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
     if (impl == 3) {
         mlp_bwd_data3_kernel<<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);

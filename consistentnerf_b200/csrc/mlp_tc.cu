@@ -574,6 +574,20 @@ int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, c
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 }
 
+// Kernel generation selected once per process.  Forward (CNERF_MLP_IMPL): default 3 = single-CTA N=256 kernel (mlp_fwd3.cu);
+// kept for A/B runs: 4 = CTA-pair ping-pong kernel (mlp_fwd4.cu, correct but slower), 1 = first-generation serial
+// kernel.  Backward data chain (CNERF_BWD_IMPL): default 3, 1 = first generation.  Only the streams in use are packed.
+static int fwd_impl() {
+    static int impl = 0;
+    if (!impl) { const char* ev = getenv("CNERF_MLP_IMPL"); impl = (ev && (ev[0] == '1' || ev[0] == '4')) ? ev[0] - '0' : 3; }
+    return impl;
+}
+static int bwd_impl() {
+    static int impl = 0;
+    if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
+    return impl;
+}
+
 static int upload_program(int* nblocks) {
     std::vector<BlkInfo> prog = build_program();
     if ((int)prog.size() > kMaxBlocks) return set_error(CNERF_EINVAL, "program too long");
@@ -629,14 +643,17 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     p.w[8] = feature_w; p.b[8] = feature_b; p.w[9] = views_w; p.b[9] = views_b;
     p.alpha_w = alpha_w; p.alpha_b = alpha_b; p.rgb_w = rgb_w; p.rgb_b = rgb_b;
     for (int i = 0; i < kNumLayers; ++i) p.ld[i] = kLayerLd[i];
-    pack_weights_kernel<<<w->num_blocks, 256, 0, as_stream(stream)>>>(p, w->stream);
-    CNERF_LAUNCH_CHECK("pack_weights_kernel");
+    if (fwd_impl() == 1) {
+        pack_weights_kernel<<<w->num_blocks, 256, 0, as_stream(stream)>>>(p, w->stream);
+        CNERF_LAUNCH_CHECK("pack_weights_kernel");
+    }
     pack_misc_kernel<<<ceil_div(kMiscFloats, 256), 256, 0, as_stream(stream)>>>(p, w->misc);
     CNERF_LAUNCH_CHECK("pack_misc_kernel");
-    int rc = pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
-    if (rc == CNERF_OK) rc = pack_stream3(p, w->stream3, as_stream(stream));
-    if (rc == CNERF_OK) rc = pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream));
-    if (rc == CNERF_OK) rc = pack_stream4(p, w->stream4, as_stream(stream));
+    int rc = CNERF_OK;
+    if (fwd_impl() == 3) rc = pack_stream3(p, w->stream3, as_stream(stream));
+    if (fwd_impl() == 4) rc = pack_stream4(p, w->stream4, as_stream(stream));
+    if (rc == CNERF_OK) rc = bwd_impl() == 3 ? pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream))
+                                             : pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
     if (rc != CNERF_OK) return rc;
     w->packed = true;
     return CNERF_OK;
@@ -651,14 +668,8 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     CNERF_REQUIRE(np64 < (int64_t)1 << 30, "%s: too many points in one call (%lld)", who, (long long)np64);
     if (np64 == 0) return CNERF_OK;
     static bool attr_set = false;
-    static bool use_v1 = false;
-    static int impl = 3;
+    const int impl = fwd_impl();
     if (!attr_set) {
-        // default 3: single-CTA N=256 kernel (mlp_fwd3.cu); kept for A/B runs: 4 = CTA-pair ping-pong kernel (mlp_fwd4.cu,
-        // correct but slower: measured in profiles/), 1 = first-generation serial kernel
-        const char* ev = getenv("CNERF_MLP_IMPL");
-        if (ev && (ev[0] == '1' || ev[0] == '4')) impl = ev[0] - '0';
-        use_v1 = impl == 1;
         cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
 

@@ -51,6 +51,27 @@ def full(src, dst):
             if h in ("Kernel Name",) or any(h == k or h.endswith(k) for k in KEYS):
                 f.write(f"{h} [{units[i]}]: " + " | ".join(r[i][:60] for r in data) + "\n")
     print(open(dst).read())
+    # per-kernel DRAM traffic per launch (mean over the captured launches) for bench.py's roofline.traffic
+    import json, os, re
+    ci = {h: i for i, h in enumerate(hdr)}
+    def col(name):
+        return next(i for h, i in ci.items() if h == name or h.endswith(name))
+    def to_bytes(v, unit):
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+        return float(v.replace(",", "")) * scale
+    kn, rd, wr, du = col("Kernel Name"), col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), col("gpu__time_duration.sum")
+    agg = {}
+    for r in data:
+        name = re.sub(r"^void ", "", r[kn]).split("(")[0].split("<")[0]
+        a = agg.setdefault(name, {"launches": 0, "dram_bytes": 0.0})
+        a["launches"] += 1
+        a["dram_bytes"] += to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr])
+    path = os.path.join(os.path.dirname(dst), "ncu_traffic.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    for k, a in agg.items():
+        old[k] = {"dram_bytes_per_launch": a["dram_bytes"] / a["launches"], "launches_captured": a["launches"], "source": os.path.basename(dst)}
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    print("updated", path)
 
 
 if __name__ == "__main__":
