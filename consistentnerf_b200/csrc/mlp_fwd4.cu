@@ -14,15 +14,14 @@
 //             (scripts/pair_layout.py), i.e. 128 columns per tile, all four lane quarters busy in the epilogue
 //   SMEM      per tile: operand [64 rows x 256 k] fp16 hi | lo (64 KB) + encoding [64 x 64] (16 KB); 8-stage ring of 8 KB
 //             half-blocks (twice the depth of fwd3 in time); every layer's blocks are streamed once per tile
-//   training  a dedicated warp streams every finished operand tile to the activation record with TMA tensor stores
-//             (box = 8 k-group rows x this CTA's 1024-byte half of the 2048-byte record rows); the record layout is the
-//             one mlp_bwd_tc.cu reads, unchanged.
+// Inference only (opt-in with CNERF_MLP_IMPL=4; training always runs mlp_fwd3.cu).  Measured slower than the single-CTA kernel
+// (DESIGN.md section 3): with synchronous tcgen05.mma issue the per-block overhead of the issuing warps sits behind instructions
+// half as long, and 8 KB half-blocks make the weight ring no deeper in time.  Kept as the parity-tested record of that experiment.
 #include "mlp_blocks.cuh"
-#include <cuda.h>
 
 namespace cnerf {
 
-constexpr int k4Threads = 672;                     // 16 epilogue warps; 16/19 loaders, 17/20 MMA issuers (peer CTA: forwarders) of tile X / Y; 18 record streamer
+constexpr int k4Threads = 672;                     // 16 epilogue warps; 16/19 loaders, 17/20 MMA issuers (peer CTA: forwarders) of tile X / Y; warp 18 idle
 constexpr uint32_t k4LBO = 1024;                   // 64 rows x 16 B between k-groups of an operand tile
 constexpr uint32_t k4ActBytes = 65536, k4ActLo = 32768;       // per tile: hi 32 KB | lo 32 KB (32 k-groups each)
 constexpr uint32_t k4Emb = 131072, k4EmbBytes = 16384, k4EmbLo = 8192;   // per tile: hi 8 KB | lo 8 KB (8 k-groups each)
@@ -31,7 +30,7 @@ constexpr int k4Stages = 8;
 constexpr uint32_t k4StageBytes = 8192;            // this CTA's half of a weight block: hi 4 KB | lo 4 KB
 constexpr uint32_t k4Bars = k4Ring + k4Stages * k4StageBytes;     // 229376
 constexpr uint32_t k4BarFull = k4Bars, k4BarEmpty = k4Bars + 64, k4BarPFull = k4Bars + 128, k4BarDFull = k4Bars + 192,
-                   k4BarAReady = k4Bars + 208, k4BarALocal = k4Bars + 224, k4BarSrd = k4Bars + 240, k4TmemSlot = k4Bars + 256;
+                   k4BarAReady = k4Bars + 208, k4TmemSlot = k4Bars + 256;
 constexpr uint32_t k4Smem = k4Bars + 320;
 constexpr uint32_t k4TmemCols = 256;               // two tiles x 128 columns
 
@@ -86,21 +85,14 @@ __device__ __forceinline__ void emit4(uint32_t hi_base, uint32_t lo_off, uint32_
     st_shared_v4(a, h[0], h[1], h[2], h[3]);
     st_shared_v4(a + lo_off, l[0], l[1], l[2], l[3]);
 }
-// TMA tensor store: box (512 u16 x 8 rows) of shared memory -> record rows [y, y + 8), columns [x, x + 512)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, uint32_t x, uint32_t y) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y) : "memory");
-}
-
 __device__ unsigned long long g_prof4[16];
 __device__ int g_prof4_on;
 __device__ int g_dbg4;          // timing experiments only (results become wrong): 1 = no waiting on weight blocks, 2 = commit only once per layer
 #define PROF4_T0() long long pt0__ = g_prof4_on ? clock64() : 0
 #define PROF4_ADD(var) do { if (g_prof4_on) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
 
-template <bool kSave>
 __global__ void __launch_bounds__(k4Threads, 1)
-mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __restrict__ wstream, const float* __restrict__ misc,
+mlp_fused4_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc,
                   const float* __restrict__ pts, const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays,
                   float* __restrict__ raw) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -108,10 +100,9 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int num_super = (n_points + 255) / 256, num_tiles = (n_points + 127) / 128;
+    const int num_super = (n_points + 255) / 256;
     const uint32_t bar_full = sbase + k4BarFull, bar_empty = sbase + k4BarEmpty, bar_pfull = sbase + k4BarPFull;
-    const uint32_t bar_dfull = sbase + k4BarDFull, bar_aready = sbase + k4BarAReady, bar_alocal = sbase + k4BarALocal;
-    const uint32_t bar_srd = sbase + k4BarSrd;
+    const uint32_t bar_dfull = sbase + k4BarDFull, bar_aready = sbase + k4BarAReady;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k4TmemSlot);
 
     if (threadIdx.x == 0) {
@@ -119,8 +110,6 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_dfull + 8 * t, 1);
             mbar_init(bar_aready + 8 * t, 32);       // 16 epilogue warps of each CTA (used in the leader only)
-            mbar_init(bar_alocal + 8 * t, 16);
-            mbar_init(bar_srd + 8 * t, 1);
         }
         fence_barrier_init();
     }
@@ -233,48 +222,6 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
             atomicAdd(&g_prof4[1], (unsigned long long)pw_a); atomicAdd(&g_prof4[3], (unsigned long long)pw_full);
             atomicAdd(&g_prof4[4], (unsigned long long)pw_issue);
         }
-    } else if (warp == 18) {
-        // ===== record streamer (training): every finished operand tile -> activation record =====
-        if (kSave && lane == 0) {
-            const uint32_t x0 = rank * 512;                               // this CTA's half of the 1024-u16 record rows
-            int sl = 0;
-            for (int S = pair; S < num_super; S += npairs, ++sl)
-                for (int j = 0; j < 11; ++j)
-                    for (int t = 0; t < 2; ++t) {
-                        mbar_wait(bar_alocal + 8 * t, (uint32_t)(sl * 11 + j) & 1);
-                        const int T = 2 * S + t;
-                        if (T < num_tiles) {
-                            const uint32_t r0 = (uint32_t)T * (uint32_t)(kTileBytes / 2048);
-                            const uint32_t act = sbase + (uint32_t)t * k4ActBytes, emb = sbase + k4Emb + (uint32_t)t * k4EmbBytes;
-                            if (j == 0) {                                 // E: point encoding
-                                tma_store_2d(&rec_map, emb, x0, r0 + (uint32_t)(kSlotE / 2048));
-                                tma_store_2d(&rec_map, emb + k4EmbLo, x0, r0 + (uint32_t)(kSlotE / 2048) + 8);
-                            } else if (j <= 9) {                          // H0..H7, F: 32 k-groups hi + 32 lo
-                                const uint32_t row = r0 + (uint32_t)(kSlotH0 / 2048) + (uint32_t)(j - 1) * 64;
-#pragma unroll 1
-                                for (uint32_t bx = 0; bx < 4; ++bx) {
-                                    tma_store_2d(&rec_map, act + bx * 8192, x0, row + bx * 8);
-                                    tma_store_2d(&rec_map, act + k4ActLo + bx * 8192, x0, row + 32 + bx * 8);
-                                }
-                                if (j == 6) {                             // V: the encoding tile now holds the direction encoding
-                                    tma_store_2d(&rec_map, emb, x0, r0 + (uint32_t)(kSlotV / 2048));
-                                    tma_store_2d(&rec_map, emb + k4EmbLo, x0, r0 + (uint32_t)(kSlotV / 2048) + 8);
-                                }
-                            } else {                                      // HV: 16 k-groups hi + 16 lo
-                                const uint32_t row = r0 + (uint32_t)(kSlotHV / 2048);
-                                tma_store_2d(&rec_map, act, x0, row);
-                                tma_store_2d(&rec_map, act + 8192, x0, row + 8);
-                                tma_store_2d(&rec_map, act + k4ActLo, x0, row + 16);
-                                tma_store_2d(&rec_map, act + k4ActLo + 8192, x0, row + 24);
-                            }
-                            bulk_commit();
-                            bulk_wait_read0();
-                        }
-                        mbar_arrive(bar_srd + 8 * t);
-                    }
-            bulk_wait0();
-        }
-        __syncwarp();
     } else if (warp < 16) {
         // ===== prologue + epilogue warps =====
         // epilogue mapping: TMEM lane quarter q -> local row 32 (q & 1) + lane, column half h = q >> 1; p -> 32 of its 128 columns
@@ -302,13 +249,12 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
                 default: enc8<56>(x, 63, e8); e8[7] = 1.f; break;      // column 63: the constant 1 that carries the biases
             }
         };
-        auto publish = [&](int t, bool local) {                           // operands of the next layer of tile t are in shared memory
+        auto publish = [&](int t) {                           // operands of the next layer of tile t are in shared memory
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_cluster(ar0 + 8 * t);
-                if (kSave && local) mbar_arrive(bar_alocal + 8 * t);
             }
         };
 
@@ -320,9 +266,8 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
             // ---- prologue: publish the (pre-computed) point encodings of both tiles
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                if (kSave && sl > 0) mbar_wait(bar_srd + 8 * t, (uint32_t)((sl - 1) * 11 + 10) & 1);
                 emit4(sbase + k4Emb + (uint32_t)t * k4EmbBytes, k4EmbLo, prow, pkg, enc[t]);
-                publish(t, true);
+                publish(t);
             }
 #pragma unroll 1
             for (int L = 0; L < 9; ++L) {
@@ -330,7 +275,6 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
                 for (int t = 0; t < 2; ++t) {
                     { PROF4_T0(); mbar_wait(bar_dfull + 8 * t, (uint32_t)(sl * 10 + L) & 1); PROF4_ADD(pw_d); }
                     tc_fence_after();
-                    if (kSave) mbar_wait(bar_srd + 8 * t, (uint32_t)(sl * 11 + L) & 1);
                     if (L == 5 && tid < 256) {
                         // every MMA of layer 5 of this tile (the last reader of point-encoding columns 0-31) is done: k-groups 0-3
                         // take the direction encoding (column 31 = 1.0 for the bias), published by this layer's arrivals
@@ -374,7 +318,7 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
                     const uint32_t abase = sbase + (uint32_t)t * k4ActBytes;
 #pragma unroll
                     for (uint32_t k4 = 0; k4 < 4; ++k4) if (!(g_dbg4 & 8)) emit4(abase, k4ActLo, irow, (c0 >> 3) + k4, v + 8 * k4);
-                    publish(t, true);
+                    publish(t);
                 }
             }
             // the next super-tile's encodings are computed while the tensor cores work on the views layers
@@ -384,7 +328,6 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
                 // views layer: ReLU (bias already in the accumulator), then rgb_linear as an fp32 dot product; 16 of 128 columns per thread
                 { PROF4_T0(); mbar_wait(bar_dfull + 8 * t, (uint32_t)(sl * 10 + 9) & 1); PROF4_ADD(pw_d); }
                 tc_fence_after();
-                if (kSave) mbar_wait(bar_srd + 8 * t, (uint32_t)(sl * 11 + 9) & 1);
                 const uint32_t c0 = (uint32_t)h * 64 + (uint32_t)p * 16;
                 float v[16];
                 tmem_ld16(t_lane + (uint32_t)t * 128 + (uint32_t)p * 16, v);
@@ -397,14 +340,6 @@ mlp_fused4_kernel(const __grid_constant__ CUtensorMap rec_map, const uint8_t* __
                     r1 = fmaf(hv, __ldg(misc + kMiscRgbW + 128 + c0 + j), r1);
                     r2 = fmaf(hv, __ldg(misc + kMiscRgbW + 256 + c0 + j), r2);
                     v[j] = fminf(hv, 65504.f);
-                }
-                if (kSave) {      // stage hv in the operand tile (its last reader, this layer's MMAs, is done) for the record streamer
-                    const uint32_t abase = sbase + (uint32_t)t * k4ActBytes;
-                    emit4(abase, k4ActLo, irow, (c0 >> 3), v);
-                    emit4(abase, k4ActLo, irow, (c0 >> 3) + 1, v + 8);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_alocal + 8 * t);
                 }
                 // partial sums of the two narrow heads -> scratch in this tile's encoding buffer (free: its last readers were the
                 // views-layer MMAs and, in training, record stores that completed before the one waited for above)
@@ -451,45 +386,13 @@ int pack_stream4(const RawParams& p, uint8_t* stream4, cudaStream_t st) {
 }
 size_t stream4_bytes() { return (size_t)2 * k3NumBlocks * k4StageBytes; }
 
-namespace {
-typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn4 encode_tiled_fn4() {
-    static EncodeTiledFn4 fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn4>(p);
-    }
-    return fn;
-}
-}  // namespace
-
 int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, const float* viewdirs, int n_points,
-                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st) {
+                  int n_samples, int n_rays, float* raw, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4Smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused4_kernel)");
         attr_set = true;
-    }
-    CUtensorMap map;
-    memset(&map, 0, sizeof(map));
-    if (acts) {
-        // record buffer as [rows][1024 x u16] (2048-byte k-group rows of 128 points); box = 8 rows x 512 u16 (this CTA's 64 points)
-        EncodeTiledFn4 fn = encode_tiled_fn4();
-        if (!fn) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-        const uint64_t rows = (uint64_t)ceil_div(n_points, 128) * (kTileBytes / 2048);
-        cuuint64_t gdim[2] = {1024, rows};
-        cuuint64_t gstride[1] = {2048};
-        cuuint32_t box[2] = {512, 8};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, acts, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled(record) failed (%d)", (int)r);
     }
     const int num_super = ceil_div(n_points, 256);
     const int pairs = num_super < kNumSMs / 2 ? num_super : kNumSMs / 2;
@@ -499,8 +402,7 @@ int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, c
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = acts ? cudaLaunchKernelEx(&cfg, mlp_fused4_kernel<true>, map, stream4, misc, pts, viewdirs, n_points, n_samples, n_rays, raw)
-                         : cudaLaunchKernelEx(&cfg, mlp_fused4_kernel<false>, map, stream4, misc, pts, viewdirs, n_points, n_samples, n_rays, raw);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_fused4_kernel, stream4, misc, pts, viewdirs, n_points, n_samples, n_rays, raw);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(mlp_fused4_kernel)");
     return CNERF_OK;
 }

@@ -569,7 +569,7 @@ int stream3_blocks();
 int pack_stream4(const RawParams& p, uint8_t* stream4, cudaStream_t st);                                // mlp_fwd4.cu
 size_t stream4_bytes();
 int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, const float* viewdirs, int n_points,
-                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
+                  int n_samples, int n_rays, float* raw, cudaStream_t st);
 int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 }
@@ -650,8 +650,8 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     pack_misc_kernel<<<ceil_div(kMiscFloats, 256), 256, 0, as_stream(stream)>>>(p, w->misc);
     CNERF_LAUNCH_CHECK("pack_misc_kernel");
     int rc = CNERF_OK;
-    if (fwd_impl() == 3) rc = pack_stream3(p, w->stream3, as_stream(stream));
-    if (fwd_impl() == 4) rc = pack_stream4(p, w->stream4, as_stream(stream));
+    if (fwd_impl() != 1) rc = pack_stream3(p, w->stream3, as_stream(stream));
+    if (rc == CNERF_OK && fwd_impl() == 4) rc = pack_stream4(p, w->stream4, as_stream(stream));
     if (rc == CNERF_OK) rc = bwd_impl() == 3 ? pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream))
                                              : pack_bwd_stream(p, w->stream_bwd, w->num_blocks_bwd, as_stream(stream));
     if (rc != CNERF_OK) return rc;
@@ -679,9 +679,9 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     int n_points = (int)np64;
     int tiles = ceil_div(n_points, (int)kRows);
     int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (impl == 4)
-        return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
-    if (impl == 3)
+    if (impl == 4 && !acts)      // the CTA-pair experiment is inference only; training runs the single-CTA kernel
+        return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, as_stream(stream));
+    if (impl != 1)
         return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     if (acts)
         mlp_fused_kernel<true><<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(w->stream, w->misc, pts, viewdirs, n_points,

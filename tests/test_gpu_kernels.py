@@ -379,3 +379,37 @@ def test_masked_loss_all_ones_mask_and_backward(cn):
         got.backward()
         assert_close(got, ref.float(), 1e-6, 0)
         assert rel_err(p.grad, p64.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# opt-in kernel generations (selected once per process by an environment variable -> run in a subprocess)
+# ------------------------------------------------------------------------------------------
+_IMPL_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, os.path.join(os.getcwd(), "tests")); sys.path.insert(0, os.getcwd())
+import consistentnerf_b200 as cn
+from oracle import nerf_oracle as O
+from util import ARCH, module_from_params, rel_err
+p = O.make_params(7, sigma_bias=0.3, **ARCH)
+net = module_from_params(p, ARCH)
+packed = net.packed_weights(); packed.refresh(dict(zip(net.spec.param_names(), [q.detach() for q in net.hot_params()])))
+worst = 0.0
+for n, S in ((1, 1), (3, 64), (40, 192), (257, 33), (700, 64)):
+    g = torch.Generator().manual_seed(n * 100 + S)
+    pts = torch.randn(n, S, 3, generator=g) * 1.5
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    raw = cn.ops.fused_mlp_forward(packed, pts.cuda(), vd.cuda())
+    ref = O._query({k: v.double() for k, v in p.items()}, ARCH, pts.double(), vd.double(), 10, 4)
+    worst = max(worst, rel_err(raw, ref))
+print("WORST", worst)
+assert worst < 2e-5, worst
+"""
+
+
+@pytest.mark.parametrize("env", [{"CNERF_MLP_IMPL": "4"}, {"CNERF_MLP_IMPL": "1"}])
+def test_opt_in_forward_kernels_match_the_oracle(env):
+    """CNERF_MLP_IMPL=4: CTA-pair ping-pong kernel (mlp_fwd4.cu); =1: first-generation serial kernel."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _IMPL_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
