@@ -177,7 +177,7 @@ def run_b200(args):
               ndc=False, lindisp=False, near=NEAR, far=FAR)
     hot = [p for net in (coarse, fine) for n_, p in net.named_parameters() if n_ in net.spec.param_names()]
     flat = FlatGrads(hot) if train else None
-    opt = torch.optim.Adam(hot, lr=5e-4, betas=(0.9, 0.999)) if train else None
+    opt = torch.optim.Adam(hot, lr=5e-4, betas=(0.9, 0.999), fused=True) if train else None      # one multi-tensor kernel per step
 
     n_batches = 8                                              # distinct batches, rotated
     host = [tuple(x.pin_memory() for x in make_batch(N_RAYS, 100 * rank + b)) for b in range(n_batches)]

@@ -386,6 +386,7 @@ def fused_mlp_forward(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.
     return raw
 
 
+ACCUMULATE_IN_PLACE = os.environ.get("CNERF_GRAD_INPLACE", "1") != "0"      # see FusedMLPFn.backward
 BWD_CHUNK_POINTS = 1 << 18      # activation recompute granularity of the CUDA-core backward pass
 MLP_BWD = os.environ.get("CNERF_MLP_BWD", "tc")      # "tc": tcgen05 backward, "simt": fp32 CUDA-core backward
 
@@ -401,11 +402,14 @@ def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: 
 
 
 def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw: torch.Tensor, n_points: int,
-                       return_record: bool = False):
-    """Parameter gradients of the canonical network from d_raw [n_points,4] and the forward's activation record."""
+                       return_record: bool = False, accumulate_into: Optional[dict] = None):
+    """Parameter gradients of the canonical network from d_raw [n_points,4] and the forward's activation record.
+    ``accumulate_into`` (name -> contiguous fp32 tensor): add the gradients to these buffers (the parameters' .grad)
+    instead of returning fresh tensors."""
     dev = acts.device
     d_raw = _f32c(d_raw).reshape(n_points, 4)
-    grads = {k: torch.empty_like(v) for k, v in P.items()}
+    acc = int(accumulate_into is not None)
+    grads = accumulate_into if acc else {k: torch.empty_like(v) for k, v in P.items()}
     lib = _lib.load()
     rec = torch.empty(int(lib.cnerf_mlp_grads_bytes(n_points)), device=dev, dtype=torch.uint8)
     ws = _workspace(dev, int(lib.cnerf_mlp_bwd_workspace_bytes()))
@@ -414,10 +418,10 @@ def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw
     st = stream()
     call("cnerf_mlp_bwd_data", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, ptr(ws), st)
     call("cnerf_mlp_bwd_heads", ptr(d_raw), ptr(acts), n_points, ptr(grads["alpha_linear.weight"]),
-         ptr(grads["alpha_linear.bias"]), ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), 0, ptr(ws), st)
+         ptr(grads["alpha_linear.bias"]), ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), acc, ptr(ws), st)
     call("cnerf_mlp_bwd_weights", ptr(acts), ptr(rec), n_points, pw, pb, ptr(grads["feature_linear.weight"]),
          ptr(grads["feature_linear.bias"]), ptr(grads["views_linears.0.weight"]), ptr(grads["views_linears.0.bias"]),
-         0, ptr(ws), st)
+         acc, ptr(ws), st)
     if return_record:
         return grads, rec
     return grads
@@ -435,6 +439,7 @@ class FusedMLPFn(torch.autograd.Function):
         packed.refresh(P)
         pts_c, vd_c = _f32c(pts.detach()), _f32c(viewdirs.detach())
         ctx.spec, ctx.P, ctx.enc, ctx.packed = spec, P, (multires, multires_views), packed
+        ctx.params = params                      # the leaf tensors themselves: backward() may add straight into their .grad
         ctx.tc = MLP_BWD == "tc" and any(ctx.needs_input_grad[6:])
         if ctx.tc:
             raw, acts = fused_mlp_forward_train(packed, pts_c, vd_c)
@@ -455,6 +460,15 @@ class FusedMLPFn(torch.autograd.Function):
             packed = ctx.packed
             if packed._key != ctx.pack_key:
                 raise RuntimeError("parameters were modified in place between the forward and the backward pass")
+            # Every parameter already owns a gradient buffer (e.g. distributed.FlatGrads, or any step after the first with
+            # zero_grad(set_to_none=False)): the reduction kernels add into it -- what autograd's AccumulateGrad would do with
+            # 24 fresh tensors and 24 add kernels per network -- and autograd receives no gradient for these inputs.
+            leaves = ctx.params
+            if ACCUMULATE_IN_PLACE and all(
+                    p.is_leaf and p.requires_grad and p.grad is not None and p.grad.dtype == _F32 and p.grad.is_contiguous()
+                    and p.grad.device == p.device and not p._backward_hooks for p in leaves):
+                fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points, accumulate_into={k: p.grad for k, p in zip(names, leaves)})
+                return (None,) * (6 + len(names))
             grads = fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points)
             return (None, None, None, None, None, None) + tuple(grads[k] for k in names)
         L, Lv = ctx.enc

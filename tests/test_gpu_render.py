@@ -149,6 +149,32 @@ def test_training_gradients_match_oracle_autograd(cn):
             assert cand < max(5e-4, 2.0 * floor), (name, cand, floor)
 
 
+def test_gradients_accumulate_into_existing_grad_buffers(cn):
+    """Parameters that already own a .grad (FlatGrads, or zero_grad(set_to_none=False)): the reduction kernels add into it and
+    autograd gets no gradient for them; the result must equal what AccumulateGrad produces from returned tensors."""
+    from consistentnerf_b200.distributed import FlatGrads
+    n = 64
+    o, d = workload_rays(n, seed=4)
+    pc, pf = O.make_params(2, sigma_bias=0.5, **ARCH), O.make_params(3, sigma_bias=0.5, **ARCH)
+    tgt = torch.rand(n, 3, generator=torch.Generator().manual_seed(6)).to(DEV)
+
+    def run(in_place, passes):
+        coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+        hot = [p for net in (coarse, fine) for nm, p in net.named_parameters() if nm in net.spec.param_names()]
+        if in_place:
+            flat = FlatGrads(hot)
+            flat.flat.fill_(2.0 ** -27)           # pre-existing content (of the gradients' own magnitude) must be kept and added to
+        kw = _kwargs(cn, coarse, fine)
+        for _ in range(passes):
+            rgb, disp, acc, depth, ex = cn.render(1, n, None, chunk=4096, rays=(o.to(DEV), d.to(DEV)), retraw=True, **kw)
+            (cn.img2mse(rgb, tgt) + cn.img2mse(ex["rgb0"], tgt)).backward()
+        return [p.grad.clone() for p in hot]
+
+    ref, got = run(False, 2), run(True, 2)
+    for a, b in zip(ref, got):
+        assert rel_err(b - 2.0 ** -27, a) < 1e-5
+
+
 def test_whole_image_render_from_pose(cn):
     """render(c2w=...) path of render_path (NP/run_nerf_view.py:270): rays generated on the device."""
     H = W = 20
