@@ -1,0 +1,117 @@
+"""Parity at BASELINE.json's full size -- 4096 rays x (64 coarse + 128 fine) samples, the workload bench.py times -- through
+properties that do not need the oracle to render 4096 rays:
+
+* every kernel on the path is per-ray, so a full-size run restricted to a random subset of rays must equal the fp64 oracle
+  run on that subset alone (the oracle finishes 64 rays in seconds);
+* the reference's own contract that results are chunk invariant (batchify_rays, NP/run_nerf.py:55-67) and, stronger,
+  invariant under any permutation of the rays -- bit for bit, because a point's arithmetic never depends on its tile mates;
+* run-to-run determinism of outputs and gradients (fixed MMA issue order, fixed reduction trees);
+* sortedness of the merged fine samples, non-negative weights that sum to acc_map, z_std >= 0;
+* additivity of the parameter gradients over ray subsets (sum-type loss).
+"""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from util import ARCH, module_from_params, rel_err, workload_rays
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+N, S_C, S_F = 4096, 64, 128
+
+
+@pytest.fixture(scope="module")
+def cn():
+    import consistentnerf_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def scene(cn):
+    pc, pf = O.make_params(0, sigma_bias=0.5, **ARCH), O.make_params(1, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    embed_fn, _ = cn.get_embedder(10, 0)
+    embeddirs_fn, _ = cn.get_embedder(4, 0)
+
+    def query(inputs, viewdirs, network_fn):
+        return cn.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn)
+    kw = dict(network_query_fn=query, perturb=0.0, N_importance=S_F, network_fine=fine, N_samples=S_C, network_fn=coarse,
+              use_viewdirs=True, white_bkgd=True, raw_noise_std=0.0, ndc=False, lindisp=False, near=2.0, far=6.0)
+    o, d = workload_rays(N)
+    return dict(pc=pc, pf=pf, coarse=coarse, fine=fine, kw=kw, o=o, d=d)
+
+
+def _render(cn, scene, o, d, chunk=32768, **over):
+    kw = dict(scene["kw"], **over)
+    rgb, disp, acc, depth, ex = cn.render(1, o.shape[0], None, chunk=chunk, rays=(o.to(DEV), d.to(DEV)), retraw=True, **kw)
+    return dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, **ex)
+
+
+@pytest.fixture(scope="module")
+def full(cn, scene):
+    with torch.no_grad():
+        return _render(cn, scene, scene["o"], scene["d"])
+
+
+def test_full_size_subset_equals_oracle_on_the_subset(cn, scene, full):
+    idx = torch.randperm(N, generator=torch.Generator().manual_seed(11))[:64]
+    o, d = scene["o"][idx].double(), scene["d"][idx].double()
+    rays = O.pack_rays(o, d, 2.0, 6.0, True)
+    p64 = lambda p: {k: v.double() for k, v in p.items()}
+    ref = O.render_rays(rays, p64(scene["pc"]), p64(scene["pf"]), ARCH, n_samples=S_C, n_importance=S_F, white_bkgd=True)
+    ref32 = O.render_rays(rays.float(), scene["pc"], scene["pf"], ARCH, n_samples=S_C, n_importance=S_F, white_bkgd=True)
+    for k in ("rgb_map", "acc_map", "depth_map", "rgb0", "acc0", "depth0"):
+        e, e32 = rel_err(full[k][idx.to(DEV)], ref[k]), rel_err(ref32[k], ref[k])
+        assert e < max(1e-4, 2 * e32), (k, e, e32)          # north-star bar: 1e-4 relative, adjudicated against fp64
+
+
+def test_full_size_is_chunk_and_permutation_invariant_bit_for_bit(cn, scene, full):
+    with torch.no_grad():
+        chunked = _render(cn, scene, scene["o"], scene["d"], chunk=1000)          # ragged last chunk (4096 = 4 x 1000 + 96)
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(12))
+        permuted = _render(cn, scene, scene["o"][perm], scene["d"][perm])
+    for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "rgb0", "depth0", "z_std", "raw"):
+        assert torch.equal(torch.nan_to_num(chunked[k]), torch.nan_to_num(full[k])), k
+        assert torch.equal(torch.nan_to_num(permuted[k]), torch.nan_to_num(full[k][perm.to(DEV)])), k
+
+
+def test_full_size_sample_and_weight_invariants(cn, scene):
+    rays = cn.ops.pack_rays(scene["o"].to(DEV), scene["d"].to(DEV), 2.0, 6.0, True)
+    t_vals = cn.ops.unit_linspace(S_C, DEV)
+    z, pts = cn.ops.stratified(rays, t_vals, torch.rand(N, S_C, device=DEV), False)
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and float(z.min()) >= 2.0 and float(z.max()) <= 6.0
+    raw = torch.randn(N, S_C, 4, device=DEV)
+    rgb, disp, acc, weights, depth = cn.raw2outputs(raw, z, rays[:, 3:6], 0.0, True)
+    assert bool((weights >= 0).all()) and rel_err(weights.sum(-1), acc) < 1e-5 and float(acc.max()) <= 1.0 + 1e-5
+    z_samples, z_fine, z_std = cn.ops.sample_fine(z, weights, torch.rand(N, S_F, device=DEV), S_F)
+    assert z_fine.shape == (N, S_C + S_F)
+    assert bool((z_fine[:, 1:] >= z_fine[:, :-1]).all())                           # merged samples are sorted along every ray
+    merged, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
+    assert torch.equal(merged, z_fine)                                             # ... and are exactly the multiset union
+    assert bool((z_std >= 0).all()) and bool((z_samples >= z[:, :1]).all()) and bool((z_samples <= z[:, -1:]).all())
+
+
+def test_full_size_training_step_is_deterministic_and_additive(cn, scene):
+    """Sum-type loss over 4096 rays: gradients of two identical runs are bit-identical, and equal the sum over four ray
+    quarters (each quarter rendered alone) to fp32 summation accuracy."""
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(13)).to(DEV)
+    names = scene["fine"].spec.param_names()
+
+    def grads(sel):
+        for net in (scene["coarse"], scene["fine"]):
+            for p in net.parameters():
+                p.grad = None
+        out = _render(cn, scene, scene["o"][sel], scene["d"][sel])
+        loss = ((out["rgb_map"] - tgt[sel.to(DEV)]) ** 2).sum() + ((out["rgb0"] - tgt[sel.to(DEV)]) ** 2).sum()
+        loss.backward()
+        return {f"{tag}.{n}": p.grad.clone() for tag, net in (("coarse", scene["coarse"]), ("fine", scene["fine"]))
+                for n, p in net.named_parameters() if n in names}
+
+    everything = torch.arange(N)
+    a, b = grads(everything), grads(everything)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    parts = [grads(everything[q * 1024:(q + 1) * 1024]) for q in range(4)]
+    for k in a:
+        total = sum(p[k].double() for p in parts)
+        assert rel_err(a[k], total) < 5e-5, k
