@@ -206,11 +206,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # e2e: every step's result (loss / rgb) is copied to pinned host memory inside the timed region; the copies are asynchronous
+    # (two pinned slots, an event per slot guards reuse) so the host keeps issuing the next step, as a training loop that logs
+    # every i_print steps does; the last results are awaited before the clock stops
+    res_slots, res_events = [None, None], [None, None]
+
+    def read_back(r, k):
+        i = k & 1
+        if res_events[i] is not None:
+            res_events[i].synchronize()
+        if res_slots[i] is None or res_slots[i].shape != r.shape:
+            res_slots[i] = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+        res_slots[i].copy_(r.detach(), non_blocking=True)
+        res_events[i] = torch.cuda.Event()
+        res_events[i].record()
+
     def timed(e2e: bool):
         for w in range(args.warmup):
             r = step(tuple(x.to(dev, non_blocking=True) for x in host[w % n_batches]) if e2e else resident[w % n_batches])
             if e2e:
-                r.cpu()
+                read_back(r, w)
         sync_all()
         _lib.launch_count = 0
         _lib.event_trace.clear()
@@ -222,7 +237,7 @@ def run_b200(args):
         for k in range(args.steps):
             if e2e:
                 r = step(tuple(x.to(dev, non_blocking=True) for x in host[k % n_batches]))
-                r.cpu()                                         # loss (train) or rgb (render) back on the host
+                read_back(r, k)                                 # loss (train) or rgb (render) back on the host
             else:
                 l2_flush.zero_()                                # flush L2 between timed iterations
                 step(resident[k % n_batches])
