@@ -27,9 +27,7 @@ __device__ int g_dbg3;          // timing experiments only (results become wrong
 
 constexpr int k3Threads = 576;                           // 16 epilogue warps + loader warp + MMA warp
 constexpr uint32_t k3ActHi = 0, k3ActLo = 65536;         // 32 k-groups x 2048 B each
-constexpr uint32_t k3EmbHi = 131072, k3EmbLo = 147456;   // 8 k-groups each; k-groups 4-7 of the LO half double as scratch
-constexpr uint32_t k3SAlpha = k3EmbLo + 8192;            // float[4][128]      (valid from layer 7 on)
-constexpr uint32_t k3SRgb = k3SAlpha + 2048;             // float[3][3][128]   (layer 9)
+constexpr uint32_t k3EmbHi = 131072, k3EmbLo = 147456;   // 8 k-groups each
 constexpr uint32_t k3Ring = 163840;
 constexpr int k3Stages = 4;
 constexpr uint32_t k3Bars = k3Ring + k3Stages * kBlockBytes;      // 229376
@@ -76,8 +74,6 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     const uint32_t bar_eready = bar_aready + 64;                 //      encoding tile written (16 warp arrivals)
     const uint32_t bar_hv = bar_eready + 8;                      //      training: views-layer output staged in SMEM
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k3TmemSlot);
-    float* s_alpha = reinterpret_cast<float*>(smem + k3SAlpha);
-    float* s_rgb = reinterpret_cast<float*>(smem + k3SRgb);
     const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
 
     if (threadIdx.x == 0) {
@@ -119,6 +115,15 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         uint32_t it = 0;
         long long pw_a = 0, pw_full = 0, pw_e = 0, pw_issue = 0, p_start = kProf ? clock64() : 0;
         int tl = 0;
+        auto store_hv = [&](uint8_t* rec_of_tile, uint32_t tl_of_tile) {      // whole warp; record slot HV of a finished tile
+            mbar_wait(bar_hv, tl_of_tile & 1);
+            if (elect_one()) {
+                bulk_s2g_hint(rec_of_tile + kSlotHV, sbase + k3ActHi, 32768, stream_pol);
+                bulk_s2g_hint(rec_of_tile + kSlotHV + 32768, sbase + k3ActLo, 32768, stream_pol);
+                bulk_commit();
+            }
+            __syncwarp();
+        };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
             { PROF_T0(); mbar_wait(bar_eready, (uint32_t)tl & 1); PROF_ADD(pw_e); }
@@ -146,6 +151,9 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         }
                         __syncwarp();
                     }
+                    // the previous tile's views output must leave the activation tile before this tile's first epilogue rewrites it
+                    // (bulk_wait_read0 ahead of the commit below): stored here, after layer 0's MMAs were issued
+                    if (kSave && layer == 0 && tl > 0 && j + 1 == nb) store_hv(rec - (size_t)gridDim.x * kTileBytes, (uint32_t)(tl - 1));
                     const uint32_t s = it % k3Stages, ph = (it / k3Stages) & 1;
                     { PROF_T0(); mbar_wait(bar_full + 8 * s, ph); PROF_ADD(pw_full); }
                     tc_fence_after();
@@ -208,15 +216,9 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     __syncwarp();
                 }
             }
-            if (kSave) {      // views-layer output, staged in the (now free) activation tile by the last epilogue
-                mbar_wait(bar_hv, (uint32_t)tl & 1);
-                if (elect_one()) {
-                    bulk_s2g_hint(rec + kSlotHV, sbase + k3ActHi, 32768, stream_pol);
-                    bulk_s2g_hint(rec + kSlotHV + 32768, sbase + k3ActLo, 32768, stream_pol);
-                    bulk_commit();
-                }
-                __syncwarp();
-            }
+            // training: this tile's views-layer output (staged in the activation tile by the last epilogue) is stored after the NEXT
+            // tile's layer-0 MMAs have been issued (store_hv below), so that layer 0 overlaps the last epilogue; the final tile here
+            if (kSave && tile + (int)gridDim.x >= num_tiles) store_hv(rec, (uint32_t)tl);
         }
         if (kSave) { if (elect_one()) bulk_wait0(); __syncwarp(); }
         if (kProf && lane == 0) {
@@ -246,16 +248,17 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         };
         float encv[16];
         if ((int)blockIdx.x < num_tiles) encode(blockIdx.x, encv);
+        auto publish_encoding = [&]() {       // the (pre-computed) point encoding of the next tile to run -> encoding tile
+            emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p, encv);
+            emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p + 1, encv + 8);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_eready);
+        };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int grow = tile * (int)kRows + (int)row;
             const bool valid = grow < n_points;
-            {   // publish the (pre-computed) point encoding
-                emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p, encv);
-                emit_kgroup<false>(eh, el, nullptr, 0, row, 2 * (uint32_t)p + 1, encv + 8);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_eready);
-            }
+            if (tl == 0) publish_encoding();      // later tiles: published at the end of the previous tile, ahead of its last epilogue
             float alpha_acc = 0.f;
 #pragma unroll 1
             for (int layer = 0; layer < 9; ++layer) {
@@ -312,13 +315,21 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
                     }
                 }
-                if (layer == 7) s_alpha[p * 128 + row] = alpha_acc;
             }
             // the next tile's encoding is computed while the tensor core works on the views layer
-            if (tile + (int)gridDim.x < num_tiles) encode(tile + (int)gridDim.x, encv);
+            const bool has_next = tile + (int)gridDim.x < num_tiles;
+            if (has_next) encode(tile + (int)gridDim.x, encv);
             {   // views layer: ReLU (bias already in the accumulator), then rgb_linear as an fp32 dot product; 32 of 128 columns per thread
                 { PROF_T0(); mbar_wait(bar_dfull + 8, (uint32_t)(tl * 5 + 4) & 1); PROF_ADD(pw_d); }
                 tc_fence_after();
+                // Every reader of the encoding tile (the views-layer MMAs were the last) is done: hand the NEXT tile's encoding to the
+                // MMA warp first, so that its layer 0 runs while these warps finish this tile (the views accumulator D[1] is not
+                // written again before layer 1, which waits for these same warps).
+                if (has_next) publish_encoding();
+                // scratch for the head reductions: the upper half of the activation tile's hi part (free since the views-layer MMAs;
+                // training stages hv in k-groups 0-15 only; the next writer is the next tile's first epilogue, after the barrier below)
+                float* s_rgb = reinterpret_cast<float*>(smem + k3ActHi + 32768);
+                float* s_alpha = s_rgb + 1152;
                 const uint32_t c = (uint32_t)p * 32;
                 float v[32];
                 tmem_ld32(t_lane + 256 + c, v);
@@ -340,6 +351,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     if (lane == 0) mbar_arrive(bar_hv);
                 }
                 if (p > 0) { float* o = s_rgb + (p - 1) * 384; o[row] = r0; o[128 + row] = r1; o[256 + row] = r2; }
+                s_alpha[p * 128 + row] = alpha_acc;
                 named_bar_sync(1, 512);
                 if (p == 0 && valid) {
                     float4 o;
@@ -350,7 +362,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     *reinterpret_cast<float4*>(raw + 4 * (size_t)grow) = o;
                 }
                 tc_fence_before();
-                named_bar_sync(1, 512);      // the scratch aliases the encoding tile the next prologue rewrites
+                named_bar_sync(1, 512);      // the scratch lives in the activation tile the next tile's first epilogue rewrites
             }
         }
         if (kProf && lane == 0 && warp == 0) {

@@ -19,13 +19,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires: waiting warps do not burn
+// issue slots (and power -- the training step runs into the board's power cap) on a polling loop
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must abort the kernel, never hang the GPU.
@@ -230,9 +232,9 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 // wait on a LOCAL mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope); bounded like mbar_wait
