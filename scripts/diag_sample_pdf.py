@@ -1,3 +1,4 @@
+"""Diagnostic: cnerf_sample_pdf debug outputs (cdf, below) against the golden vectors and the host oracle (ISA dependence of torch.sum)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
