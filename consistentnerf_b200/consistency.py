@@ -92,17 +92,28 @@ def build_hard_masks(rays_o_views: Sequence[torch.Tensor], rays_d_views: Sequenc
     return masks
 
 
-def masked_img_loss(rgb, target, mask, hardmask_coef: float, n_rand: Optional[int] = None):
-    """img2mse(rgb[mask==1], target[mask==1]) + [mask.sum() != N_rand] * coef * img2mse(... mask==0)."""
+def masked_img_loss(rgb, target, mask, hardmask_coef: float, n_rand: Optional[int] = None, return_stats: bool = False):
+    """img2mse(rgb[mask==1], target[mask==1]) + [mask.sum() != N_rand] * coef * img2mse(... mask==0).
+    ``return_stats``: also the kernel's 5 device scalars [loss, #mask==1, #mask==0, plain img2mse over all rows, sum(mask)] --
+    the quantities train() logs every step (NP/run_nerf_view.py:1908-1924) come out of the same launch, see ``loss_scalars``."""
     n_ref = float(rgb.shape[0] if n_rand is None else n_rand)
-    loss, _ = ops.MaskedMSEFn.apply(rgb, target, mask, 1.0, float(hardmask_coef), n_ref, True)
-    return loss
+    loss, stats = ops.MaskedMSEFn.apply(rgb, target, mask, 1.0, float(hardmask_coef), n_ref, True)
+    return (loss, stats) if return_stats else loss
+
+
+def loss_scalars(stats: torch.Tensor, prefix: str = "") -> dict:
+    """Named 0-d device tensors from a K7 stats vector: masked loss and its PSNR, plain MSE and its PSNR (mse2psnr,
+    NP/run_nerf_helpers.py:11), mask population.  No host synchronisation: feed them to pipeline.StepLog."""
+    s = stats.detach()
+    to_psnr = lambda x: -10.0 * torch.log(x) / 2.302585092994046
+    return {prefix + "masked_loss": s[0], prefix + "masked_psnr": to_psnr(s[0]), prefix + "mse": s[3], prefix + "psnr": to_psnr(s[3]),
+            prefix + "n_masked": s[1]}
 
 
 def masked_depth_loss(depth_pred, depth_prior, mask, far: float, hardmask_coef: float = 0.0,
-                      n_rand: Optional[int] = None, include_unmasked: bool = False):
+                      n_rand: Optional[int] = None, include_unmasked: bool = False, return_stats: bool = False):
     """img2mse(d[mask==1]/far, prior[mask==1]/far) (+ coef * unmasked term in the cal_correspondance recipe)."""
     n_ref = float(depth_pred.shape[0] if n_rand is None else n_rand)
-    loss, _ = ops.MaskedMSEFn.apply(depth_pred.reshape(-1, 1), depth_prior.reshape(-1, 1), mask, float(far),
-                                    float(hardmask_coef), n_ref, bool(include_unmasked))
-    return loss
+    loss, stats = ops.MaskedMSEFn.apply(depth_pred.reshape(-1, 1), depth_prior.reshape(-1, 1), mask, float(far),
+                                        float(hardmask_coef), n_ref, bool(include_unmasked))
+    return (loss, stats) if return_stats else loss

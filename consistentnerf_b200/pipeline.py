@@ -5,6 +5,9 @@
   the full image every step, then gathers ``N_rand`` pixels with numpy indices.  Here every view lives on the device once;
   a step draws the view on the host (one integer), the pixel ids on the device, and one kernel emits the packed rays and
   the gathered targets of exactly those pixels.
+* ``StepLog``     -- the per-step scalar logging of train() (NP/run_nerf_view.py:1908-1937): ten-odd ``add_scalar(tensor)`` calls per
+  step, each a device synchronisation.  Here the scalars stay on the device in a ring of rows and reach the host with one
+  copy every ``i_print`` steps.
 * ``render_path`` -- the novel-view image loop (NP/run_nerf_view.py:252-294): images are rendered back to back while the
   previous image's device->host copy runs on a side stream into pinned double buffers; same return value
   ``(rgbs, disps, accs)`` as the reference.
@@ -20,7 +23,7 @@ import torch
 from . import ops
 from .nerf import to8b
 
-__all__ = ["RayBank", "render_path"]
+__all__ = ["RayBank", "render_path", "StepLog"]
 
 
 class RayBank:
@@ -70,6 +73,49 @@ class RayBank:
             self.depths[view] if self.depths is not None else None, self.masks[view] if self.masks is not None else None)
         return {"rays": rays, "batch_rays": torch.stack([rays[:, 0:3], rays[:, 3:6]], 0), "target": target, "depth": depth,
                 "mask": mask, "pix": pix, "view": view}
+
+
+class StepLog:
+    """Per-step training scalars without per-step host synchronisation.
+
+        log = StepLog(["loss", "psnr", "psnr0"], capacity=100)
+        log.record(i, loss=loss, **loss_scalars(stats))      # 0-d device tensors (or Python floats); stream ordered, no sync
+        if i % i_print == 0:
+            for step, row in log.flush():                    # ONE device->host copy for everything recorded since the last flush
+                writer.add_scalar(...)
+    """
+
+    def __init__(self, names: Sequence[str], capacity: int = 1024, device="cuda"):
+        self.names = list(names)
+        self.col = {n: j for j, n in enumerate(self.names)}
+        self.capacity = int(capacity)
+        self.buf = torch.full((self.capacity, len(self.names)), float("nan"), device=device, dtype=torch.float32)
+        self.steps = []
+
+    def record(self, step: int, **scalars):
+        if len(self.steps) >= self.capacity:
+            raise RuntimeError("StepLog is full: call flush() at least every `capacity` steps")
+        row = self.buf[len(self.steps)]
+        for name, v in scalars.items():
+            j = self.col.get(name)
+            if j is None:
+                continue                                    # not a logged quantity
+            if isinstance(v, torch.Tensor):
+                row[j:j + 1].copy_(v.detach().reshape(1), non_blocking=True)
+            else:
+                row[j] = float(v)
+        self.steps.append(int(step))
+
+    def flush(self):
+        """[(step, {name: float})] of every record since the last flush; one device->host copy."""
+        n = len(self.steps)
+        if n == 0:
+            return []
+        host = self.buf[:n].cpu().numpy()
+        out = [(st, {name: float(host[i, j]) for name, j in self.col.items()}) for i, st in enumerate(self.steps)]
+        self.buf[:n].fill_(float("nan"))
+        self.steps = []
+        return out
 
 
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, render_fn=None):

@@ -245,3 +245,27 @@ def test_render_path_matches_per_image_render(cn):
             rgb, disp, acc, depth, _ = cn.render(H, W, K, chunk=4096, c2w=poses[k][:3, :4].to(DEV), **kw)
             assert np.array_equal(rgbs[k], rgb.cpu().numpy()) and np.array_equal(accs[k], acc.cpu().numpy())
             np.testing.assert_array_equal(disps[k], disp.cpu().numpy())
+
+
+def test_step_log_and_loss_scalars_without_per_step_sync(cn):
+    """The per-step logging of train() (NP/run_nerf_view.py:1908-1937): the logged quantities come out of the loss kernel's
+    own statistics and reach the host once per flush; values must equal the reference formulas."""
+    g = torch.Generator().manual_seed(21)
+    log = cn.StepLog(["loss", "mse", "psnr", "masked_psnr", "n_masked"], capacity=8)
+    expect = []
+    for step in range(5):
+        rgb, tgt = torch.rand(300, 3, generator=g), torch.rand(300, 3, generator=g)
+        mask = (torch.rand(300, 1, generator=g) > 0.4).float()
+        loss, stats = cn.masked_img_loss(rgb.to(DEV), tgt.to(DEV), mask.to(DEV), 0.2, return_stats=True)
+        log.record(step, loss=loss, not_logged=1.0, **cn.loss_scalars(stats))
+        mse = ((rgb - tgt) ** 2).mean()
+        m1 = mask[:, 0] == 1
+        ref_loss = O.masked_mse(rgb, tgt, mask, 0.2, 300)
+        expect.append(dict(loss=float(ref_loss), mse=float(mse), psnr=float(-10.0 * torch.log(mse) / np.log(10.0)),
+                           n_masked=float(m1.sum())))
+    rows = log.flush()
+    assert [s for s, _ in rows] == list(range(5)) and log.flush() == []
+    for (_, got), ref in zip(rows, expect):
+        for k, v in ref.items():
+            assert abs(got[k] - v) <= 2e-5 * max(1.0, abs(v)), (k, got[k], v)
+        assert np.isfinite(got["masked_psnr"])
