@@ -48,6 +48,7 @@ SIGNATURES = {
     "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
     "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_debug_profile4": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_profile_chain": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_umma_selftest_pair": (_I, [_P, _P, _I, _I, _P, _P]),

@@ -330,6 +330,12 @@ __device__ __forceinline__ void emit_g(uint32_t hi_base, uint32_t lo_base, uint3
     st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
 }
 
+__device__ unsigned long long g_profc[16];
+#define PROFC_T0() long long pt0__ = kProf ? clock64() : 0
+#define PROFC_ADD(var) do { if (kProf) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
+
+// kProf: instrumented instantiation for the phase profile (cnerf_debug_profile_chain); the production kernel carries none of it
+template <bool kProf>
 __global__ void __launch_bounds__(kC3Threads, 1)
 mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
                      const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
@@ -379,6 +385,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         const uint64_t stream_pol = l2_policy_evict_first();
         uint32_t it = 0;
         int tl = 0;
+        long long pw_a = 0, pw_full = 0, pw_issue = 0, p_start = kProf ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             uint8_t* grec = grads + (size_t)tile * kGTileBytes;
             // every k-block of an operand tile (G of some layer) is streamed to the gradient record as soon as it is final
@@ -398,13 +405,14 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                     if (!(j & 1)) {
                         const int kb = j >> 1;
                         const uint32_t aph = kb < 4 ? (uint32_t)(tl * 10 + step) & 1 : (uint32_t)(tl * 9 + step - 1) & 1;
-                        mbar_wait(bar_aready + 8 * kb, aph);
+                        { PROFC_T0(); mbar_wait(bar_aready + 8 * kb, aph); PROFC_ADD(pw_a); }
                         if (elect_one()) store_kblock(9 - step, kb);
                         __syncwarp();
                     }
                     const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
+                    { PROFC_T0(); mbar_wait(bar_full + 8 * s, ph); PROFC_ADD(pw_full); }
                     tc_fence_after();
+                    PROFC_T0();
                     if (elect_one()) {
                         const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
                         const uint64_t ah = act_hi + (uint64_t)(j * kStep), al = act_lo + (uint64_t)(j * kStep);
@@ -418,6 +426,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                         }
                     }
                     __syncwarp();
+                    PROFC_ADD(pw_issue);
                 }
             }
             // G0, written by the last epilogue, has no consumer here: store it and release the tile to the next prologue
@@ -432,6 +441,11 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         }
         if (elect_one()) bulk_wait0();
         __syncwarp();
+        if (kProf && lane == 0) {
+            atomicAdd(&g_profc[0], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_profc[1], (unsigned long long)pw_a); atomicAdd(&g_profc[3], (unsigned long long)pw_full);
+            atomicAdd(&g_profc[4], (unsigned long long)pw_issue);
+        }
     } else {
         // ===== prologue + epilogue warps: thread = (row, p); per 32-column k-block it owns columns 8p..8p+7 =====
         const int q = warp & 3, p = warp >> 2;
@@ -440,6 +454,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
         const uint32_t ah = sbase + kC3ActHi, al = sbase + kC3ActLo;
         const float scale = grad_scale(amax_bits);
         int tl = 0;
+        long long pw_d = 0, pw_s = 0, p_start = kProf ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int grow = tile * (int)kRows + (int)row;
             const bool valid = grow < n_points;
@@ -447,7 +462,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
             float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
             dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
-            if (tl > 0) mbar_wait(bar_sdone, (uint32_t)(tl - 1) & 1);        // the previous tile's G0 has left the operand tile
+            if (tl > 0) { PROFC_T0(); mbar_wait(bar_sdone, (uint32_t)(tl - 1) & 1); PROFC_ADD(pw_s); }      // the previous tile's G0 has left the operand tile
             // G9 = (d_rgb W_rgb) * [hv > 0]: four k-blocks of 32 columns
             uint4 mhv[4];                                                     // ReLU masks of the views layer: all four loads in flight at once
 #pragma unroll
@@ -484,7 +499,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                     for (uint32_t kb = 0; kb < 8; ++kb)
                         mk[kb] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(kb * 4 + p) * 2048 + row * 16));
                 }
-                mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1);
+                { PROFC_T0(); mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1); PROFC_ADD(pw_d); }
                 tc_fence_after();
                 const uint32_t dcol = t_lane + (uint32_t)(step & 1) * 256 + (uint32_t)p * 8;
 #pragma unroll
@@ -524,6 +539,10 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                 }
             }
             tc_fence_before();
+        }
+        if (kProf && lane == 0 && warp == 0) {
+            atomicAdd(&g_profc[8], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_profc[9], (unsigned long long)pw_d); atomicAdd(&g_profc[10], (unsigned long long)pw_s);
         }
     }
     tc_fence_before();
@@ -915,7 +934,8 @@ int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, vo
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
         attr_set = true;
@@ -934,6 +954,19 @@ int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, vo
 }
 }  // namespace
 
+static int g_profc_host = 0;
+// Debug: in-kernel phase profile of mlp_bwd_data3_kernel (cycles summed over CTAs):
+//  [0] MMA warp total  [1] wait operand k-blocks  [3] wait weights  [4] MMA issue + commit  [8] epilogue total  [9] wait D  [10] wait G0 stored
+extern "C" int cnerf_debug_profile_chain(int enable, unsigned long long* out16) {
+    unsigned long long zero[16] = {0};
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_profc, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_profc, zero, sizeof(zero));
+    if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile_chain");
+    g_profc_host = enable & 1;
+    return CNERF_OK;
+}
+
 // Stage 1: gradient scale + data-gradient chain -> grads_rec (G tiles of every layer).
 extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec,
                                   int n_points, void* workspace, void* stream) {
@@ -951,7 +984,8 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     static int impl = 0;      // same selection as cnerf_weights_refresh (mlp_tc.cu: bwd_impl), which packs only the stream in use
     if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
     if (impl == 3) {
-        mlp_bwd_data3_kernel<<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+        if (g_profc_host) mlp_bwd_data3_kernel<true><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+        else mlp_bwd_data3_kernel<false><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
         CNERF_LAUNCH_CHECK("mlp_bwd_data3_kernel");
         return CNERF_OK;
     }

@@ -25,3 +25,17 @@ for mode, dbg in ([("infer", 0), ("infer", 1)] if IMPL == "4" else [("infer", 0)
     print("impl", IMPL, mode, "dbg", dbg, "128-point tiles per SM %.1f" % tiles)
     for k, nm in names.items():
         print(f"   {nm:20s} {out[k] / 148 / 1e3:10.1f} kcycles/CTA   {out[k] / 148 / tiles:10.0f} cycles/tile")
+
+# ---- data-gradient chain kernel (training backward)
+raw, acts = cn.ops.fused_mlp_forward_train(packed, pts, vd)
+P = dict(zip(net.spec.param_names(), [p.detach() for p in net.hot_params()]))
+d_raw = torch.randn(n * S, 4, device=dev) * 1e-6
+for _ in range(2): cn.ops.fused_mlp_backward(packed, P, acts, d_raw, n * S)
+out = (ctypes.c_ulonglong * 16)()
+_lib.call("cnerf_debug_profile_chain", 1, out)
+cn.ops.fused_mlp_backward(packed, P, acts, d_raw, n * S)
+_lib.call("cnerf_debug_profile_chain", 0, out)
+tiles = n * S / 128 / 148
+print("chain3 128-point tiles per SM %.1f" % tiles)
+for k, nm in {0: "mma total", 1: "mma wait A kblocks", 3: "mma wait weights", 4: "mma issue+commit", 8: "epilogue total", 9: "epilogue wait D", 10: "epilogue wait G0 stored"}.items():
+    print(f"   {nm:24s} {out[k] / 148 / 1e3:10.1f} kcycles/CTA   {out[k] / 148 / tiles:10.0f} cycles/tile")
