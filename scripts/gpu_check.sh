@@ -15,3 +15,6 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'mlp_fused3_kernel|mlp_bwd_data3_kernel' --launch-skip 8 -c 4 -f -o $OUT/prof_fwd_chain_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full1_$TAG.log 2>&1; echo "ncu full fwd/chain rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'mlp_bwd_weight_kernel' --launch-skip 40 -c 3 -f -o $OUT/prof_dw_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full2_$TAG.log 2>&1; echo "ncu full dw rc=$?"
 ls -la $OUT
+CNERF_MLP_IMPL=3 timeout 200 python scripts/prof_phases.py > $OUT/prof_phases_$TAG.txt 2>&1; echo "phase profile rc=$?"
+timeout 200 python scripts/umma_rate.py > $OUT/umma_rate_$TAG.txt 2>&1; echo "umma rate rc=$?"
+timeout 200 python scripts/host_time.py 2>&1 | head -4 > $OUT/host_time_$TAG.txt; echo "host time rc=$?"
