@@ -29,7 +29,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_RAYS, N_SAMPLES, N_IMPORTANCE = 4096, 64, 128
 FLOP_PER_POINT = 1_186_816
@@ -74,8 +73,30 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_rays(n, seed=0):
+    """Workload A of SURVEY.md section 8(d): o = (0,0,4) + 0.1 N(0,1), d = normalize((0,0,-1) + 0.2 N(0,1)), near 2, far 6."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([0.0, 0.0, 4.0]) + 0.1 * torch.randn(n, 3, generator=g)
+    d = torch.tensor([0.0, 0.0, -1.0]) + 0.2 * torch.randn(n, 3, generator=g)
+    return o, d / d.norm(dim=-1, keepdim=True)
+
+
+def make_nets(dev):
+    """Coarse and fine NeRF(D=8, W=256, 63 + 27 inputs, viewdirs) with the reference's default initialisation under seeds 0 / 1
+    and the density-head bias shifted by 0.5 ("trained-like": a non-uniform sample_pdf).  Built from the
+    product's own module -- the B200 arm never touches oracle/."""
+    import consistentnerf_b200 as cn
+    nets = []
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        net = cn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        with torch.no_grad():
+            net.alpha_linear.bias += 0.5
+        nets.append(net.to(dev))
+    return nets
+
+
 def make_batch(n, seed):
-    from util import workload_rays
     o, d = workload_rays(n, seed)
     g = torch.Generator().manual_seed(seed + 1000)
     tgt = torch.rand(n, 3, generator=g)
@@ -161,12 +182,9 @@ def run_b200(args):
     import consistentnerf_b200 as cn
     from consistentnerf_b200 import _lib
     from consistentnerf_b200.distributed import FlatGrads
-    from oracle import nerf_oracle as O                        # parameters + cpu_baseline leg only
-    from util import ARCH, module_from_params
 
     train = args.mode == "train"
-    pc, pf = O.make_params(0, sigma_bias=0.5, **ARCH), O.make_params(1, sigma_bias=0.5, **ARCH)
-    coarse, fine = module_from_params(pc, ARCH, dev), module_from_params(pf, ARCH, dev)
+    coarse, fine = make_nets(dev)
     embed_fn, _ = cn.get_embedder(10, 0)
     embeddirs_fn, _ = cn.get_embedder(4, 0)
 
@@ -312,8 +330,8 @@ def run_b200(args):
 # reference arm: CPU oracle port of the reference path
 # ----------------------------------------------------------------------------------------------
 def run_reference(args, sample_rays=256, steps=None, warmup=None, quiet=False):
-    from oracle import nerf_oracle as O
-    from util import ARCH
+    from oracle import nerf_oracle as O          # the reference arm / cpu_baseline leg is the one place bench.py executes oracle/
+    ARCH = dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=(4,), use_viewdirs=True)
     steps = args.steps if steps is None else steps
     warmup = args.warmup if warmup is None else warmup
     cores = os.cpu_count() or 1

@@ -142,7 +142,7 @@ umma_bench_pair_kernel(int iters, int traffic, const uint8_t* __restrict__ src, 
         uint32_t x = (i + 77u * blockIdx.x) * 2654435761u;            // traffic bit 4: pseudo-random fp16 pairs in (-2, 2) instead of zeros
         reinterpret_cast<uint32_t*>(smem)[i] = (traffic & 16) ? ((x & 0x83ff83ffu) | 0x3c003c00u) : 0u;
     }
-    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 24, 1); for (int s = 0; s < 4; ++s) mbar_init(rbar + 8 * s, 1); *stop = 0; fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 24, 1); mbar_init(bar + 64, 1); for (int s = 0; s < 4; ++s) mbar_init(rbar + 8 * s, 1); *stop = 0; fence_barrier_init(); }
     if (warp == 0) { if (kPair) tmem_alloc2(bar + 8, 512); else tmem_alloc(bar + 8, 512); }
     fence_proxy_async();
     tc_fence_before();
@@ -160,10 +160,10 @@ umma_bench_pair_kernel(int iters, int traffic, const uint8_t* __restrict__ src, 
                 ad[ks] = smem_desc(a_s + ks * 2 * kLBO);
             }
             long long t0 = clock64();
-            if (threadIdx.x == 0) mbar_arrive(bar + 28 + 4);      // bar + 32 = rbar[0] is unused unless the bulk ring runs: complete its phase 0
+            if (threadIdx.x == 0) mbar_arrive(bar + 64);          // a completed barrier for the per-group wait experiment
             __syncwarp();
             for (int i = 0; i < iters; i += 4) {
-                if (traffic & 32) mbar_wait_cluster(bar + 32, 0);            // the fused kernel's per-block waits and fence
+                if (traffic & 32) mbar_wait_cluster(bar + 64, 0);            // the fused kernel's per-block waits and fence
                 if (traffic & 64) tc_fence_after();
                 if (elect_one()) {
                     if (kPair && (traffic & 8)) {           // the fused kernel's pattern: 3 MMAs on one accumulator + a multicast commit

@@ -1,12 +1,10 @@
+"""Host enqueue time of one training step vs its GPU time (is the step host bound?) + a cProfile of the enqueue path."""
 import os, sys, time, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, consistentnerf_b200 as cn
 from consistentnerf_b200.distributed import FlatGrads
-from oracle import nerf_oracle as O
-from util import ARCH, module_from_params
 dev = torch.device("cuda", 0)
-pc, pf = O.make_params(0, sigma_bias=0.5, **ARCH), O.make_params(1, sigma_bias=0.5, **ARCH)
-coarse, fine = module_from_params(pc, ARCH, dev), module_from_params(pf, ARCH, dev)
+coarse, fine = bench.make_nets(dev)
 embed_fn, _ = cn.get_embedder(10, 0); embeddirs_fn, _ = cn.get_embedder(4, 0)
 def query(i, v, f): return cn.run_network(i, v, f, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn)
 kw = dict(network_query_fn=query, perturb=1.0, N_importance=128, network_fine=fine, N_samples=64, network_fn=coarse, use_viewdirs=True, white_bkgd=True, raw_noise_std=0.0, ndc=False, lindisp=False, near=2.0, far=6.0)

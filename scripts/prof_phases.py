@@ -1,13 +1,12 @@
 """In-kernel phase profile of the fused MLP kernel (cycles averaged per CTA)."""
 import ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import consistentnerf_b200 as cn
 from consistentnerf_b200 import _lib
-from oracle import nerf_oracle as O
-from util import ARCH, module_from_params
+import bench
 dev = "cuda"
-net = module_from_params(O.make_params(0, sigma_bias=0.5, **ARCH), ARCH)
+net = bench.make_nets(torch.device(dev))[0]
 packed = net.packed_weights(); packed.refresh(dict(zip(net.spec.param_names(), [p.detach() for p in net.hot_params()])))
 n, S = 4096, 192
 pts = torch.randn(n, S, 3, device=dev); vd = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
