@@ -1,18 +1,22 @@
 // K2+K3 fused forward, third generation: N=256 MMAs, double-buffered accumulators, k-block pipelining.
 //
-// Measured on B200 (scripts/umma_rate.py): one tcgen05.mma M=128 x N=256 x K=16 runs at 128-138 cycles (93-100 % of
-// the tensor pipe) no matter what else the issuing warp does, whereas N=128 instructions are issue bound
-// (90-150 cycles for 64 cycles of work).  So every 256-wide layer is issued as N=256 instructions:
+// Measured on B200 (scripts/umma_rate.py, profiles/r1e_umma_issue_rate.txt): one tcgen05.mma M=128 x N=256 x K=16 runs at
+// 128 cycles (the pipe rate) back to back, N=128 costs the same 128 cycles (operand-A fetch bound), and issue is SYNCHRONOUS
+// with execution: every instruction the issuing warp executes between MMAs is added to the time per MMA.  Consequences:
+// every 256-wide layer is issued as N=256 instructions, and the issue loop carries nothing it does not need (the phase
+// profile is a separate template instantiation, kProf).
 //
 //   TMEM   two 256-column fp32 accumulators; layer L accumulates into D[L & 1]
 //   SMEM   A operand: activations of the current layer (K=256, fp16 hi/lo, 128 KB) + encoding tile (32 KB),
-//          4-stage ring of 16 KB weight blocks ([256 out-rows x 16 k], hi 8 KB + lo 8 KB)
+//          4-stage ring of 16 KB weight blocks ([256 out-rows x 16 k], hi 8 KB + lo 8 KB), fetched with the L2 evict_last policy
 //
 // The epilogue of layer L (16 warps) walks the accumulator k-block by k-block (32 columns of D = one 32-wide k-block
 // of the next layer's A operand) and signals each finished k-block through its own mbarrier; the MMA warp starts
 // layer L+1 on k-block 0 while the epilogue is still converting k-blocks 1..7 -- it writes the OTHER accumulator, so
-// the only serialisation left is the first k-block.  The training variant writes the activation record with
-// coalesced 16-byte global stores straight from the epilogue registers.
+// the only serialisation left is the first k-block.  The next tile's encoding is published ahead of the last (views-layer)
+// epilogue, so its layer 0 overlaps that epilogue.  The training variant (kSave) streams every finished A k-block to the
+// activation record with bulk S2G copies issued by the MMA warp (L2 evict_first); measured alternatives -- a dedicated
+// streaming warp, direct st.global from the epilogue -- were slower.
 #include "mlp_blocks.cuh"
 
 namespace cnerf {
