@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_void_p
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcnerf.so")
+LIB_PATH = os.environ.get("CNERF_LIB") or os.path.join(_PKG, "libcnerf.so")      # CNERF_LIB: A/B runs against another build
 
 _P = c_void_p
 _I = c_int

@@ -71,6 +71,21 @@ __device__ __forceinline__ void emit_record(uint8_t* rec_hi, size_t lo_off, uint
     st_global_v4_(rec_hi + lo_off + off, l[0], l[1], l[2], l[3]);
 }
 
+// bit j = [sign bit of w[j] clear] for eight floats: the top bytes are gathered with PRMT and the four sign bits of a word
+// are compacted with one multiply (y * (2^24 + 2^17 + 2^10 + 2^3) puts bit 8 i of y at bit 24 + i, no two terms collide)
+__device__ __forceinline__ uint32_t sign_clear_bits8(const float* w) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t a = __byte_perm(__float_as_uint(w[4 * q]), __float_as_uint(w[4 * q + 1]), 0x0073);
+        const uint32_t b = __byte_perm(__float_as_uint(w[4 * q + 2]), __float_as_uint(w[4 * q + 3]), 0x0073);
+        const uint32_t x = __byte_perm(a, b, 0x5410);
+        const uint32_t y = (~x >> 7) & 0x01010101u;
+        r |= ((y * 0x01020408u) >> 24) << (4 * q);
+    }
+    return r;
+}
+
 template <int J>
 __device__ __forceinline__ float enc_col3(const float (&x)[3], int width) {
     if (J >= width) return 0.f;

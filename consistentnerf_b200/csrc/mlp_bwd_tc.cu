@@ -464,22 +464,19 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
             dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
             if (tl > 0) { PROFC_T0(); mbar_wait(bar_sdone, (uint32_t)(tl - 1) & 1); PROFC_ADD(pw_s); }      // the previous tile's G0 has left the operand tile
             // G9 = (d_rgb W_rgb) * [hv > 0]: four k-blocks of 32 columns
-            uint4 mhv[4];                                                     // ReLU masks of the views layer: all four loads in flight at once
-#pragma unroll
-            for (uint32_t kb = 0; kb < 4; ++kb)
-                mhv[kb] = __ldg(reinterpret_cast<const uint4*>(arec + kSlotHV + (size_t)(kb * 4 + (uint32_t)p) * 2048 + row * 16));
+            // ReLU sign bits of the views layer: the row's sixteen k-group bytes in one load
+            const uint4 mrow = __ldg(reinterpret_cast<const uint4*>(arec + kSlotM + 32768 + row * 16));
+            const uint32_t mword[4] = {mrow.x, mrow.y, mrow.z, mrow.w};
 #pragma unroll
             for (uint32_t kb = 0; kb < 4; ++kb) {
                 const uint32_t kg = kb * 4 + (uint32_t)p, c = kg * 8;
-                const uint4 m = mhv[kb];
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                const uint32_t mbits = mword[kb] >> (8 * (uint32_t)p);          // byte kg = 4 kb + p of the row
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float gsum = dr.x * __ldg(misc + kMiscRgbW + c + j) + dr.y * __ldg(misc + kMiscRgbW + 128 + c + j) +
                                  dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
-                    uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
-                    v[j] = hb ? clamp_h(gsum) : 0.f;
+                    v[j] = ((mbits >> j) & 1u) ? clamp_h(gsum) : 0.f;
                 }
                 emit_g(ah, al, row, kg, v);
                 fence_proxy_async();
@@ -490,23 +487,19 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
 #pragma unroll 1
             for (int step = 0; step < 9; ++step) {
                 const int L = 9 - step;                           // D = gradient w.r.t. the input of layer L = G_{L-1} before masking
-                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;      // hi half of h_{L-1} (L <= 8)
-                // the ReLU masks do not depend on this step's MMAs: all eight loads are issued BEFORE waiting for the accumulator,
-                // so their HBM latency (the record is not L2 resident) hides behind the tensor-core work of the step
-                uint4 mk[8];
-                if (L != 9) {
-#pragma unroll
-                    for (uint32_t kb = 0; kb < 8; ++kb)
-                        mk[kb] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(kb * 4 + p) * 2048 + row * 16));
-                }
+                const uint8_t* msk = arec + kSlotM + (size_t)(L - 1) * 4096;         // ReLU sign bits of h_{L-1} (L <= 8)
+                // the sign bits do not depend on this step's MMAs: the load is issued BEFORE waiting for the accumulator, so its HBM
+                // latency (the record is not L2 resident) hides behind the tensor-core work of the step
+                uint2 mk8 = make_uint2(0u, 0u);                                        // this thread's eight bytes: k-blocks 0-3 | 4-7
+                if (L != 9) mk8 = __ldg(reinterpret_cast<const uint2*>(msk + (size_t)p * 1024 + row * 8));
                 { PROFC_T0(); mbar_wait(bar_dfull + 8 * (step & 1), (uint32_t)(tl * ((step & 1) ? 4 : 5) + (step >> 1)) & 1); PROFC_ADD(pw_d); }
                 tc_fence_after();
                 const uint32_t dcol = t_lane + (uint32_t)(step & 1) * 256 + (uint32_t)p * 8;
 #pragma unroll
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
                     float v[16];
-                    uint4 m[2];
-                    if (L != 9) { m[0] = mk[kb]; m[1] = mk[kb + 1]; }
+                    const uint32_t mw = kb < 4 ? mk8.x : mk8.y;
+                    const uint32_t m[2] = {mw >> (8 * (kb & 3)), mw >> (8 * ((kb + 1) & 3))};
                     tmem_ld8g(dcol + kb * 32, v);
                     tmem_ld8g(dcol + kb * 32 + 32, v + 8);
                     tmem_ld_wait();
@@ -520,12 +513,8 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                             w[4] = fmaf(dr.w, a1.x, w[4]); w[5] = fmaf(dr.w, a1.y, w[5]); w[6] = fmaf(dr.w, a1.z, w[6]); w[7] = fmaf(dr.w, a1.w, w[7]);
                         }
                         if (L != 9) {
-                            const uint32_t mw[4] = {m[u].x, m[u].y, m[u].z, m[u].w};
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
-                                w[j] = hb ? clamp_h(w[j]) : 0.f;
-                            }
+                            for (int j = 0; j < 8; ++j) w[j] = ((m[u] >> j) & 1u) ? clamp_h(w[j]) : 0.f;
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) w[j] = clamp_h(w[j]);
@@ -981,8 +970,13 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
-    static int impl = 0;      // same selection as cnerf_weights_refresh (mlp_tc.cu: bwd_impl), which packs only the stream in use
-    if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
+    // same selection as cnerf_weights_refresh (mlp_tc.cu: bwd_impl), which packs only the stream in use.  The first-generation
+    // forward does not write the sign-bit slot this generation's chain reads, so it pairs with the first-generation chain.
+    static int impl = 0;
+    if (!impl) {
+        const char *ev = getenv("CNERF_BWD_IMPL"), *fv = getenv("CNERF_MLP_IMPL");
+        impl = ((ev && ev[0] == '1') || (fv && fv[0] == '1')) ? 1 : 3;
+    }
     if (impl == 3) {
         if (g_profc_host) mlp_bwd_data3_kernel<true><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
         else mlp_bwd_data3_kernel<false><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);

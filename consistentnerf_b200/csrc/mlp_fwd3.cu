@@ -64,6 +64,8 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
+// (__maxnreg__(104/112) instead of the launch bound would avoid the few spills of the training variant, but 576 threads then
+// exceed the register file's allocation granularity: "too many resources requested for launch")
 template <bool kSave, bool kProf>
 __global__ void __launch_bounds__(k3Threads, 1)
 mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
@@ -284,6 +286,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     emit_kgroup<false>(eh, el, nullptr, 0, row, (uint32_t)p, v);
                 }
                 const bool relu = layer != 8;
+                uint32_t mbits_lo = 0, mbits_hi = 0;      // training: this thread's 8 sign-bit bytes of the layer (k-blocks 0-3 | 4-7)
                 const uint32_t dcol = t_lane + (uint32_t)(layer & 1) * 256 + (uint32_t)p * 8;
 #pragma unroll 1
                 for (uint32_t kb = 0; kb < 8; kb += 2) {
@@ -300,6 +303,10 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     for (int u = 0; u < 2; ++u) {
                         const uint32_t c = (kb + u) * 32 + (uint32_t)p * 8;
                         float* w = v + 8 * u;
+                        if (kSave) {              // ReLU sign bits of this k-group (byte kb + u of this thread's eight), from the pre-activations
+                            const uint32_t bits = sign_clear_bits8(w);
+                            if (kb + u < 4) mbits_lo |= bits << (8 * (kb + u)); else mbits_hi |= bits << (8 * (kb + u - 4));
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float t = relu ? fmaxf(w[j], 0.f) : fmaxf(w[j], -65504.f);
@@ -319,6 +326,9 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         if (lane == 0) mbar_arrive(bar_aready + 8 * (kb + u));
                     }
                 }
+                if (kSave && relu)        // record slot M: one 8-byte store per thread and layer (256 contiguous bytes per warp)
+                    *reinterpret_cast<uint2*>(acts + (size_t)tile * kTileBytes + kSlotM + (size_t)layer * 4096 + (size_t)p * 1024 + row * 8) =
+                        make_uint2(mbits_lo, mbits_hi);
             }
             // the next tile's encoding is computed while the tensor core works on the views layer
             const bool has_next = tile + (int)gridDim.x < num_tiles;
@@ -338,6 +348,12 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                 float v[32];
                 tmem_ld32(t_lane + 256 + c, v);
                 tmem_ld_wait();
+                if (kSave) {      // ReLU sign bits of the views-layer pre-activations: k-groups 4p..4p+3 of this row, one 4-byte store
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) word |= sign_clear_bits8(v + 8 * k4) << (8 * k4);
+                    *reinterpret_cast<uint32_t*>(acts + (size_t)tile * kTileBytes + kSlotM + 32768 + row * 16 + (c >> 3)) = word;
+                }
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -347,6 +363,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     r2 = fmaf(hv, __ldg(misc + kMiscRgbW + 256 + c + j), r2);
                     v[j] = fminf(hv, 65504.f);
                 }
+
                 if (kSave) {      // stage hv in the activation tile (its last reader, this layer's MMAs, is done)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) emit_kgroup<false>(ah, al, nullptr, 0, row, (c >> 3) + k4, v + 8 * k4);

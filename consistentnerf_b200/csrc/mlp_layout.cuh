@@ -41,7 +41,11 @@ constexpr uint32_t kSRgb = kSAlpha + 512;               // float[3][128]
 constexpr uint32_t kSmemTotal = kSRgb + 1536;           // 231552 <= 232448
 
 constexpr size_t kSlotE = 0, kSlotH0 = 32768, kSlotF = kSlotH0 + 8 * 131072, kSlotV = kSlotF + 131072,
-                 kSlotHV = kSlotV + 32768, kTileBytes = kSlotHV + 65536;      // 1 310 720 B per 128 points
+                 kSlotHV = kSlotV + 32768, kSlotM = kSlotHV + 65536, kTileBytes = kSlotM + 34816;      // 1 345 536 B per 128 points
+// kSlotM: ReLU sign bits, one byte per (row, k-group): bit j = [feature 8 kg + j > 0].  Layout follows the epilogue thread
+// mapping (thread = (row, p), k-groups kb * 4 + p for kb = 0..7) so that a thread stores / loads its eight bytes of a layer
+// with one 8-byte access:  H_l (l = 0..7): l * 4096 + p * 1024 + row * 8 + kb;  views-layer output: 32768 + row * 16 + kg.
+// The data-gradient chain reads these 34 KB per tile instead of the 544 KB of hi halves it used to scan for the same bits.
 
 constexpr int kEpiThreads = 256;
 constexpr int kThreads = kEpiThreads + 64;
@@ -51,7 +55,7 @@ constexpr uint32_t kTmemCols = 512;
 // layout) is also streamed to HBM, one record per 128-point tile; the backward kernels (mlp_bwd_tc.cu)
 // read ReLU masks and dW operands from it.  Slot = [hi | lo], each k-group 2048 B (128 rows x 16 B).
 //   E  point encoding (K=64)   H0..H7 pts_linears outputs (K=256)   F feature_linear output (K=256)
-//   V  direction encoding (K=32 used, stored as the 64-wide buffer)  HV views_linears output (K=128)
+//   V  direction encoding (K=32 used, stored as the 64-wide buffer)  HV views_linears output (K=128)   M  ReLU sign bits
 
 }  // namespace cnerf
 

@@ -584,7 +584,7 @@ static int fwd_impl() {
 }
 static int bwd_impl() {
     static int impl = 0;
-    if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = (ev && ev[0] == '1') ? 1 : 3; }
+    if (!impl) { const char* ev = getenv("CNERF_BWD_IMPL"); impl = ((ev && ev[0] == '1') || fwd_impl() == 1) ? 1 : 3; }
     return impl;
 }
 

@@ -13,8 +13,9 @@ from util import ARCH, module_from_params, rel_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-TILE = 1310720
+TILE = 1310720 + 34816          # operand slots + the ReLU sign-bit slot M
 SLOT_E, SLOT_H0, SLOT_F, SLOT_V, SLOT_HV = 0, 32768, 32768 + 8 * 131072, 32768 + 9 * 131072, 32768 + 9 * 131072 + 32768
+SLOT_M = SLOT_HV + 65536
 GTILE = 65536 + 9 * 131072
 
 
@@ -100,6 +101,30 @@ def test_activation_record(setup):
     assert rel_err(V[:, :27], ref["ev"]) < 2e-6
     HV = decode(acts, TILE, SLOT_HV, 16, 32768, n)
     assert rel_err(HV, ref["hv"]) < 5e-6
+    # ReLU sign bits (slot M), bit j of a byte = [feature 8 kg + j > 0]: H_l bytes at l * 4096 + p * 1024 + row * 8 + kb for
+    # k-group kb * 4 + p; views-layer bytes at 32768 + row * 16 + kg (what the data-gradient chain masks with).
+    rec = acts.cpu().numpy().reshape(-1, TILE)
+
+    def unpack(b):                                   # [128 rows, kgroups] bytes -> [128, 8 * kgroups] bools
+        return np.unpackbits(b[:, :, None], axis=2, bitorder="little").reshape(128, -1)
+
+    def hidden_bits(l):
+        out = []
+        for t_ in range(rec.shape[0]):
+            b = rec[t_, SLOT_M + l * 4096:SLOT_M + (l + 1) * 4096].reshape(4, 128, 8)              # [p][row][kb]
+            out.append(unpack(b.transpose(1, 2, 0).reshape(128, 32)))                                 # k-group = kb * 4 + p
+        return torch.from_numpy(np.concatenate(out, 0)[:n].astype(bool))
+
+    def same_sign(bits_, pre):          # the bits are the signs of the kernel's own fp32 pre-activations: compare away from zero
+        pre = pre.detach()
+        decided = pre.abs() > 1e-5 * pre.abs().max()
+        assert float(decided.float().mean()) > 0.999
+        assert torch.equal(bits_[decided], (pre > 0)[decided])
+
+    for l in range(8):
+        same_sign(hidden_bits(l), ref["pre"][l])
+    hvb = np.concatenate([unpack(rec[t_, SLOT_M + 32768:SLOT_M + 32768 + 2048].reshape(128, 16)) for t_ in range(rec.shape[0])], 0)
+    same_sign(torch.from_numpy(hvb[:n].astype(bool)), ref["zv"])
 
 
 def test_gradient_chain_and_parameter_gradients(setup):
