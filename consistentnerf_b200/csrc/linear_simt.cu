@@ -3,7 +3,7 @@
 // This is the any-architecture path behind the NeRF nn.Module surface (arbitrary D / W / skips /
 // use_viewdirs, NP/run_nerf_helpers.py:67-130) and the fp32 backward of the MLP.  It is a plain
 // 128x128x16 register-tiled SGEMM with fused bias / ReLU / ReLU-mask prologue; the canonical
-// 8x256 network takes the tcgen05 path in mlp_tc.cu instead.
+// 8x256 network takes the tcgen05 path (mlp_fwd3.cu / mlp_bwd_tc.cu) instead.
 #include "common.cuh"
 
 namespace cnerf {

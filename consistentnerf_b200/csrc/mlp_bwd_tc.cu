@@ -1,7 +1,7 @@
 // K3b: backward of the canonical 8x256 NeRF MLP on tcgen05 tensor cores (sm_100a).
 //
 // Inputs: d_raw [P,4] (from the compositing backward), the activation records written by the training
-// forward (mlp_tc.cu, kSave), the live weights.  Three stages, all with the forward's fp16 hi/lo split
+// forward (mlp_fwd3.cu, kSave), the live weights.  Three stages, all with the forward's fp16 hi/lo split
 // (3 MMAs per MAC, fp32 accumulation in TMEM):
 //
 //   1. mlp_bwd_data_kernel   the data-gradient chain, fused over the layers like the forward: per 128-point
@@ -20,7 +20,6 @@
 #include "mlp_layout.cuh"
 #include <cuda.h>
 #include <stdlib.h>
-#include <vector>
 
 namespace cnerf {
 
@@ -58,226 +57,10 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* 
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
 }
 
-// ------------------------------------------------------------------------------------
-// transposed weight stream for the data-gradient chain
-// ------------------------------------------------------------------------------------
-struct BwdBlk { uint8_t step, half, a_kg, first, last_of_step, wait_a, kb, pad; };   // step s <-> layer 9 - s
-__constant__ BwdBlk c_bwd_blocks[kMaxBlocks];
-__constant__ int c_num_bwd_blocks;
-
-static std::vector<BwdBlk> build_bwd_program() {
-    std::vector<BwdBlk> prog;
-    for (int step = 0; step < 9; ++step) {
-        int kblocks = step == 0 ? 4 : 8;               // G9 is 128 wide, the others 256
-        for (int h = 0; h < 2; ++h)
-            for (int kb = 0; kb < kblocks; ++kb) {
-                BwdBlk b = {};
-                b.step = (uint8_t)step; b.half = (uint8_t)h; b.a_kg = (uint8_t)(4 * kb); b.kb = (uint8_t)kb;
-                b.first = kb == 0; b.last_of_step = (h == 1 && kb + 1 == kblocks); b.wait_a = (h == 0 && kb == 0);
-                prog.push_back(b);
-            }
-    }
-    return prog;
-}
-
-// block (step, half, kb): B[r][k] = W_L[kb*32 + k][col0 + half*128 + r],  L = 9 - step, col0 = 63 for the skip layer
-__global__ void __launch_bounds__(256)
-pack_bwd_weights_kernel(RawParams p, uint8_t* __restrict__ stream) {
-    BwdBlk bi = c_bwd_blocks[blockIdx.x];
-    const int L = 9 - bi.step;
-    const float* W = p.w[L];
-    const int ld = p.ld[L], col0 = (L == 5) ? 63 : 0;
-    uint8_t* dst = stream + (size_t)blockIdx.x * kBlockBytes;
-    for (int u = threadIdx.x; u < 512; u += 256) {
-        int r = u & 127, kg = u >> 7;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = W[(size_t)(bi.kb * 32 + kg * 8 + e) * ld + col0 + bi.half * 128 + r];
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_pack2(v[2 * e], v[2 * e + 1], h[e], l[e]);
-        size_t off = (size_t)kg * kLBO + (size_t)r * 16;
-        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(dst + kBlockHalfBytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
-    }
-}
-
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
 // ------------------------------------------------------------------------------------
-// 1. data-gradient chain
-// ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-mlp_bwd_data_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
-                    const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
-                    uint8_t* __restrict__ grads) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + kBars, bar_empty = bar_full + 8 * kStages;
-    const uint32_t bar_a = bar_empty + 8 * kStages, bar_d = bar_a + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kTmemSlot);
-    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
-    const int nblk = c_num_bwd_blocks;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_a, kEpiThreads);
-        mbar_init(bar_d, 1);
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc(sbase + kTmemSlot, kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 8) {
-        // ===== weight loader =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int b = 0; b < nblk; ++b, ++it) {
-                    uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
-                    bulk_g2s(sbase + kRing + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s);
-                }
-        }
-    } else if (warp == 9) {
-        // ===== MMA issuer (also streams every finished G tile to HBM) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(128, 128);
-            uint32_t it = 0, a_cnt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                uint8_t* rec = grads + (size_t)tile * kGTileBytes;
-                for (int b = 0; b < nblk; ++b, ++it) {
-                    BwdBlk bi = c_bwd_blocks[b];
-                    if (bi.wait_a) {
-                        mbar_wait(bar_a, a_cnt & 1); ++a_cnt; tc_fence_after();
-                        if (bi.step == 0) {
-                            bulk_s2g(rec, sbase + kActHi, 32768);
-                            bulk_s2g(rec + 32768, sbase + kActLo, 32768);
-                        } else {
-                            bulk_s2g(rec + g_slot(9 - bi.step), sbase + kActHi, 131072);
-                        }
-                        bulk_commit();
-                    }
-                    uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    tc_fence_after();
-                    uint32_t a_hi = sbase + kActHi + bi.a_kg * kLBO, a_lo = sbase + kActLo + bi.a_kg * kLBO;
-                    uint32_t b_hi = sbase + kRing + s * kBlockBytes, b_lo = b_hi + kBlockHalfBytes;
-                    uint32_t d = tmem + bi.half * 128;
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 2; ++ks) {
-                        uint64_t ah = smem_desc(a_hi + ks * 2 * kLBO), al = smem_desc(a_lo + ks * 2 * kLBO);
-                        uint64_t bh = smem_desc(b_hi + ks * 2 * kLBO), bl = smem_desc(b_lo + ks * 2 * kLBO);
-                        umma_f16(d, ah, bh, idesc, (bi.first && ks == 0) ? 0u : 1u);
-                        umma_f16(d, ah, bl, idesc, 1u);
-                        umma_f16(d, al, bh, idesc, 1u);
-                    }
-                    umma_commit(bar_empty + 8 * s);
-                    if (bi.last_of_step) { bulk_wait_read0(); umma_commit(bar_d); }
-                }
-                mbar_wait(bar_a, a_cnt & 1); ++a_cnt;            // G0 written by the last epilogue
-                bulk_s2g(rec + g_slot(0), sbase + kActHi, 131072);
-                bulk_commit();
-                bulk_wait_read0();
-            }
-            bulk_wait0();
-        }
-    } else {
-        // ===== prologue + epilogue warps =====
-        const int e = warp;
-        const uint32_t row = (uint32_t)((e & 3) * 32 + lane);
-        const int part = e >> 2;
-        const uint32_t t_lane = tmem + ((uint32_t)((e & 3) * 32) << 16);
-        const float scale = grad_scale(amax_bits);
-        uint32_t d_cnt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int grow = tile * (int)kRows + (int)row;
-            const bool valid = grow < n_points;
-            const uint8_t* arec = acts + (size_t)tile * kTileBytes;
-            float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
-            dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
-            {   // G9 = (d_rgb W_rgb) * [hv > 0], 64 columns per thread
-                const uint8_t* hv = arec + kSlotHV;               // hi part: 16 k-groups
-#pragma unroll 1
-                for (int g = 0; g < 8; ++g) {
-                    const int kg = part * 8 + g, c = kg * 8;
-                    uint4 m = __ldg(reinterpret_cast<const uint4*>(hv + (size_t)kg * 2048 + row * 16));
-                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float gsum = dr.x * __ldg(misc + kMiscRgbW + c + j) + dr.y * __ldg(misc + kMiscRgbW + 128 + c + j) +
-                                     dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
-                        uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
-                        v[j] = hb ? clamp_h(gsum) : 0.f;
-                    }
-                    store_split8(sbase + kActHi, sbase + kActLo, row, kg, v);
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-            }
-            for (int step = 0; step < 9; ++step) {
-                mbar_wait(bar_d, d_cnt & 1); ++d_cnt;
-                tc_fence_after();
-                const int L = 9 - step;                           // D = gradient w.r.t. the input of layer L
-                const uint8_t* msk = arec + kSlotH0 + (size_t)(L - 1) * 131072;   // ReLU mask of that input (L <= 8)
-                const uint32_t col0 = (uint32_t)part * 128;
-#pragma unroll 1
-                for (uint32_t ch = 0; ch < 4; ++ch) {
-                    const uint32_t c = col0 + ch * 32;
-                    uint4 m[4];
-                    if (L != 9) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            m[g] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)((c >> 3) + g) * 2048 + row * 16));
-                    }
-                    float v[32];
-                    tmem_ld32(t_lane + c, v);
-                    tmem_ld_wait();
-                    if (L == 8) {                                 // + d_sigma * alpha_linear.weight
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 aw = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + j));
-                            v[j] = fmaf(dr.w, aw.x, v[j]); v[j + 1] = fmaf(dr.w, aw.y, v[j + 1]);
-                            v[j + 2] = fmaf(dr.w, aw.z, v[j + 2]); v[j + 3] = fmaf(dr.w, aw.w, v[j + 3]);
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (L != 9) {
-                            const uint32_t mw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                uint32_t hb = (mw[j >> 1] >> ((j & 1) * 16)) & 0x7fffu;
-                                v[8 * g + j] = hb ? clamp_h(v[8 * g + j]) : 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[8 * g + j] = clamp_h(v[8 * g + j]);
-                        }
-                        store_split8(sbase + kActHi, sbase + kActLo, row, (c >> 3) + g, v + 8 * g);
-                    }
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem, kTmemCols);
-}
-
-// ------------------------------------------------------------------------------------
-// 1b. data-gradient chain, N=256 / double-buffered accumulator / k-block pipelined (same structure as mlp_fwd3.cu)
+// 1. data-gradient chain (N=256 instructions, double-buffered accumulators, k-block pipelining: the forward's structure)
 // ------------------------------------------------------------------------------------
 constexpr int kC3Threads = 576;
 constexpr uint32_t kC3ActHi = 0, kC3ActLo = 65536;
@@ -852,31 +635,8 @@ __global__ void heads_reduce_kernel(const float* __restrict__ part, int n_cta, f
 
 using namespace cnerf;
 
-// defined in mlp_tc.cu
-namespace cnerf { int upload_bwd_program_once(int* nblocks); }
-
-static int g_bwd_blocks = -1;
-int cnerf::upload_bwd_program_once(int* nblocks) {
-    if (g_bwd_blocks < 0) {
-        std::vector<BwdBlk> prog = build_bwd_program();
-        if ((int)prog.size() > kMaxBlocks) return set_error(CNERF_EINVAL, "backward program too long");
-        int n = (int)prog.size();
-        cudaError_t e = cudaMemcpyToSymbol(c_bwd_blocks, prog.data(), prog.size() * sizeof(BwdBlk));
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_num_bwd_blocks, &n, sizeof(int));
-        if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbol(c_bwd_blocks)");
-        g_bwd_blocks = n;
-    }
-    *nblocks = g_bwd_blocks;
-    return CNERF_OK;
-}
-
 // called from cnerf_weights_refresh (mlp_tc.cu)
 namespace cnerf {
-int pack_bwd_stream(const RawParams& p, uint8_t* stream_bwd, int nblocks, cudaStream_t st) {
-    pack_bwd_weights_kernel<<<nblocks, 256, 0, st>>>(p, stream_bwd);
-    CNERF_LAUNCH_CHECK("pack_bwd_weights_kernel");
-    return CNERF_OK;
-}
 int bwd_stream3_blocks() { return kC3NumBlocks; }
 int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st) {
     pack_bwd_weights3_kernel<<<kC3NumBlocks, 256, 0, st>>>(p, stream);
@@ -922,8 +682,7 @@ struct BwdCtx {
 int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, void* stream, BwdCtx* c) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
@@ -959,7 +718,7 @@ extern "C" int cnerf_debug_profile_chain(int enable, unsigned long long* out16) 
 // Stage 1: gradient scale + data-gradient chain -> grads_rec (G tiles of every layer).
 extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec,
                                   int n_points, void* workspace, void* stream) {
-    CNERF_REQUIRE(w && w->packed && w->stream_bwd, "cnerf_mlp_bwd_data: weights handle not packed");
+    CNERF_REQUIRE(w && w->packed && w->stream_bwd3, "cnerf_mlp_bwd_data: weights handle not packed");
     CNERF_REQUIRE(d_raw && acts && grads_rec && workspace, "cnerf_mlp_bwd_data: null pointer");
     CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_data: negative n_points");
     if (n_points == 0) return CNERF_OK;
@@ -970,21 +729,9 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
-    // same selection as cnerf_weights_refresh (mlp_tc.cu: bwd_impl), which packs only the stream in use.  The first-generation
-    // forward does not write the sign-bit slot this generation's chain reads, so it pairs with the first-generation chain.
-    static int impl = 0;
-    if (!impl) {
-        const char *ev = getenv("CNERF_BWD_IMPL"), *fv = getenv("CNERF_MLP_IMPL");
-        impl = ((ev && ev[0] == '1') || (fv && fv[0] == '1')) ? 1 : 3;
-    }
-    if (impl == 3) {
-        if (g_profc_host) mlp_bwd_data3_kernel<true><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
-        else mlp_bwd_data3_kernel<false><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
-        CNERF_LAUNCH_CHECK("mlp_bwd_data3_kernel");
-        return CNERF_OK;
-    }
-    mlp_bwd_data_kernel<<<c.grid, kThreads, kSmemTotal, c.st>>>(w->stream_bwd, w->misc, d_raw, c.a, c.amax, n_points, c.g);
-    CNERF_LAUNCH_CHECK("mlp_bwd_data_kernel");
+    if (g_profc_host) mlp_bwd_data3_kernel<true><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+    else mlp_bwd_data3_kernel<false><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+    CNERF_LAUNCH_CHECK("mlp_bwd_data3_kernel");
     return CNERF_OK;
 }
 

@@ -6,7 +6,6 @@
 namespace cnerf {
 
 constexpr int kNumLayers = 10;                  // 0-7 pts_linears, 8 feature_linear, 9 views_linears.0
-constexpr int kMaxBlocks = 160;
 constexpr uint32_t kBlockBytes = 16384;
 constexpr uint32_t kBlockHalfBytes = 8192;
 
@@ -26,20 +25,8 @@ struct RawParams {
 };
 
 // ------------------------------------------------------------------------------------
-// shared-memory map of the fused kernel
+// activation record (training): one record per 128-point tile
 // ------------------------------------------------------------------------------------
-constexpr uint32_t kActHi = 0;                          // 32 k-groups x 2048 B  (K = 256)
-constexpr uint32_t kActLo = 65536;
-constexpr uint32_t kEmbHi = 131072;                     // 8 k-groups (K = 64): point encoding, later dir encoding
-constexpr uint32_t kEmbLo = 147456;
-constexpr uint32_t kRing = 163840;                      // 4 stages x 16 KB
-constexpr int kStages = 4;
-constexpr uint32_t kBars = kRing + kStages * kBlockBytes;      // 229376
-constexpr uint32_t kTmemSlot = kBars + 96;
-constexpr uint32_t kSAlpha = kBars + 128;               // float[128]
-constexpr uint32_t kSRgb = kSAlpha + 512;               // float[3][128]
-constexpr uint32_t kSmemTotal = kSRgb + 1536;           // 231552 <= 232448
-
 constexpr size_t kSlotE = 0, kSlotH0 = 32768, kSlotF = kSlotH0 + 8 * 131072, kSlotV = kSlotF + 131072,
                  kSlotHV = kSlotV + 32768, kSlotM = kSlotHV + 65536, kTileBytes = kSlotM + 34816;      // 1 345 536 B per 128 points
 // kSlotM: ReLU sign bits, one byte per (row, k-group): bit j = [feature 8 kg + j > 0].  Layout follows the epilogue thread
@@ -47,9 +34,6 @@ constexpr size_t kSlotE = 0, kSlotH0 = 32768, kSlotF = kSlotH0 + 8 * 131072, kSl
 // with one 8-byte access:  H_l (l = 0..7): l * 4096 + p * 1024 + row * 8 + kb;  views-layer output: 32768 + row * 16 + kg.
 // The data-gradient chain reads these 34 KB per tile instead of the 544 KB of hi halves it used to scan for the same bits.
 
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = kEpiThreads + 64;
-constexpr uint32_t kTmemCols = 512;
 
 // Training mode: every A operand (encodings and post-activation layer outputs, fp16 hi/lo in the UMMA
 // layout) is also streamed to HBM, one record per 128-point tile; the backward kernels (mlp_bwd_tc.cu)
@@ -60,13 +44,10 @@ constexpr uint32_t kTmemCols = 512;
 }  // namespace cnerf
 
 struct cnerf_weights {
-    uint8_t* stream = nullptr;      // forward weight stream: packed fp16 hi/lo blocks in program order
-    uint8_t* stream_bwd = nullptr;  // transposed blocks in the order the data-gradient chain consumes them
-    uint8_t* stream_bwd3 = nullptr; // chain stream of the N=256 backward kernel: [256 x 16] transposed blocks
-    uint8_t* stream3 = nullptr;     // forward stream of the N=256 kernel (mlp_fwd3.cu): [256 x 16] blocks
+    uint8_t* stream3 = nullptr;     // forward stream (mlp_fwd3.cu): [256 x 16] blocks, hi 8 KB | lo 8 KB, in consumption order
+    uint8_t* stream_bwd3 = nullptr; // data-gradient chain stream (mlp_bwd_tc.cu): [256 x 16] transposed blocks
     uint8_t* stream4 = nullptr;     // forward stream of the CTA-pair kernel (mlp_fwd4.cu): per block two 8 KB halves
     float* misc = nullptr;          // biases + alpha/rgb heads (fp32)
-    int num_blocks = 0, num_blocks_bwd = 0;
     int device = -1;
     bool packed = false;
 };
