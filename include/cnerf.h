@@ -126,8 +126,8 @@ int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w, const flo
 int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
                   int n_samples, float* raw, void* stream);
 /* Training-mode forward: same result as cnerf_mlp_fwd, and every layer's A operand (encodings, post-activation
- * outputs; fp16 hi/lo tiles) is streamed into `acts` (cnerf_mlp_acts_bytes(n_rays*n_samples) bytes, device) for
- * cnerf_mlp_bwd. */
+ * outputs; fp16 hi/lo tiles) plus the ReLU sign bits are streamed into `acts` (cnerf_mlp_acts_bytes(n_rays*n_samples)
+ * bytes, device: 1 345 536 per 128 points, opaque to the caller) for cnerf_mlp_bwd. */
 int64_t cnerf_mlp_acts_bytes(int64_t n_points);
 int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
                         float* raw, void* acts, void* stream);
