@@ -6,6 +6,7 @@ Drop-in for the hot path of the reference's nerf-pytorch tree behind its own fun
     NeRF / Embedder / get_embedder / sample_pdf / get_rays / ndc_rays             (nerf.py)
     get_ref_rays / get_test_label / hard masks / masked losses                    (consistency.py)
     RayBank (device-resident batch sampler) / render_path (novel-view image loop) / StepLog (sync-free logging)   (pipeline.py)
+    reference-format checkpoints / PFM depth maps / metrics.txt                   (formats.py)
 
 All arithmetic runs in libcnerf.so (hand-written CUDA, C ABI in include/cnerf.h); there is no
 PyTorch-eager or CPU fallback -- a missing library or a CPU tensor raises.
@@ -15,6 +16,7 @@ from .nerf import (NeRF, Embedder, get_embedder, sample_pdf, get_rays, get_rays_
                    to8b)
 from .render import batchify, run_network, batchify_rays, render, raw2outputs, render_rays, make_api
 from .pipeline import RayBank, render_path, StepLog
+from . import formats
 from .consistency import (get_rays_ref, get_ref_rays, get_test_label, build_hard_masks, masked_img_loss,
                           masked_depth_loss, loss_scalars)
 
