@@ -52,6 +52,8 @@ def pack_rays(rays_o, rays_d, near: float, far: float, use_viewdirs: bool, ndc=N
     o, d = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3))
     n = o.shape[0]
     out = torch.empty((n, 11 if use_viewdirs else 8), device=o.device, dtype=_F32)
+    if n == 0:
+        return out
     H, W, focal = (int(ndc[0]), int(ndc[1]), float(ndc[2])) if ndc is not None else (0, 0, 0.0)
     call("cnerf_pack_rays", ptr(o), ptr(d), n, float(near), float(far), int(use_viewdirs), int(ndc is not None),
          H, W, focal, ptr(out), stream())

@@ -87,6 +87,8 @@ def _render_rays(with_depth, ray_batch, network_fn, network_query_fn, N_samples,
     dev = ray_batch.device
     rays = ray_batch if (ray_batch.dtype == torch.float32 and ray_batch.is_contiguous()) else ray_batch.float().contiguous()
     N_rays = rays.shape[0]
+    if N_rays == 0:
+        return _empty_result(with_depth, dev, network_fn, network_fine, N_samples, N_importance, retraw)
     rays_d = rays[:, 3:6]
     viewdirs = rays[:, -3:].contiguous() if rays.shape[-1] > 8 else None
 
@@ -136,6 +138,29 @@ def _render_rays(with_depth, ray_batch, network_fn, network_query_fn, N_samples,
     return ret
 
 
+def _empty_result(with_depth, dev, network_fn, network_fine, N_samples, N_importance, retraw):
+    """render_rays on an empty ray batch: the reference's shapes ([0, ...]) with no kernel launch (a zero-sized grid is an
+    error); the tensors stay attached to the parameters so that loss.backward() yields zero gradients, as nn.Linear does
+    on an empty input."""
+    params = [p for net in (network_fn, network_fine) if isinstance(net, torch.nn.Module) for p in net.parameters() if p.requires_grad]
+    link = sum((p.reshape(-1)[:0].sum() for p in params), torch.zeros((), device=dev)) if torch.is_grad_enabled() else torch.zeros((), device=dev)
+
+    def z(*shape):
+        return torch.zeros(shape, device=dev) + link
+    S = N_samples + (N_importance if N_importance > 0 else 0)
+    ret = {"rgb_map": z(0, 3), "disp_map": z(0), "acc_map": z(0)}
+    if with_depth:
+        ret["depth_map"] = z(0)
+    if retraw:
+        ret["raw"] = z(0, S, 4)
+    if N_importance > 0:
+        ret["rgb0"], ret["disp0"], ret["acc0"] = z(0, 3), z(0), z(0)
+        if with_depth:
+            ret["depth0"] = z(0)
+        ret["z_std"] = torch.zeros((0,), device=dev)
+    return ret
+
+
 def make_api(with_depth: bool) -> types.SimpleNamespace:
     """Namespace with render / batchify_rays / render_rays of one reference flavour."""
     api = types.SimpleNamespace(batchify=batchify, run_network=run_network, raw2outputs=raw2outputs)
@@ -148,6 +173,8 @@ def make_api(with_depth: bool) -> types.SimpleNamespace:
     def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
         """NP/run_nerf.py:55-67.  Results are chunk invariant (every kernel is per-ray)."""
         all_ret = {}
+        if rays_flat.shape[0] == 0:
+            return api.render_rays(rays_flat, **kwargs)
         for i in range(0, rays_flat.shape[0], chunk):
             ret = api.render_rays(rays_flat[i:i + chunk], **kwargs)
             for k in ret:

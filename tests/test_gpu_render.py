@@ -269,3 +269,28 @@ def test_step_log_and_loss_scalars_without_per_step_sync(cn):
         for k, v in ref.items():
             assert abs(got[k] - v) <= 2e-5 * max(1.0, abs(v)), (k, got[k], v)
         assert np.isfinite(got["masked_psnr"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 129])
+def test_render_edge_sizes(cn, n):
+    """Empty, single-ray and just-over-one-tile batches through the whole path (forward and backward): shapes follow the
+    reference (leading dimension n), nothing launches a zero-sized grid, a ray rendered alone equals the same ray in a batch."""
+    o, d = workload_rays(max(n, 1), seed=9)
+    o, d = o[:n], d[:n]
+    pc, pf = O.make_params(4, sigma_bias=0.5, **ARCH), O.make_params(5, sigma_bias=0.5, **ARCH)
+    coarse, fine = module_from_params(pc, ARCH), module_from_params(pf, ARCH)
+    kw = _kwargs(cn, coarse, fine)
+    rgb, disp, acc, depth, ex = cn.render(1, n, None, chunk=4096, rays=(o.to(DEV), d.to(DEV)), retraw=True, **kw)
+    assert rgb.shape == (n, 3) and disp.shape == (n,) and acc.shape == (n,) and depth.shape == (n,)
+    assert ex["raw"].shape == (n, 192, 4) and ex["rgb0"].shape == (n, 3) and ex["z_std"].shape == (n,)
+    loss = (rgb ** 2).sum() + (ex["rgb0"] ** 2).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    for p in fine.hot_params():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+        if n == 0:
+            assert float(p.grad.abs().max()) == 0.0
+    if n == 129:
+        with torch.no_grad():
+            one = cn.render(1, 1, None, chunk=4096, rays=(o[128:129].to(DEV), d[128:129].to(DEV)), **kw)
+        assert torch.equal(one[0], rgb[128:129].detach()) and torch.equal(one[3], depth[128:129].detach())
