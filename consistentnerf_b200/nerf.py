@@ -147,6 +147,8 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
 
 # ---- hierarchical sampling (NP/run_nerf_helpers.py:206-250) -------------------------------------
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    if bins.numel() == 0:                     # empty ray batch: the reference's shape, no kernel launch
+        return torch.zeros(list(bins.shape[:-1]) + [N_samples], device=bins.device, dtype=torch.float32)
     u = None
     if pytest:
         np.random.seed(0)

@@ -48,6 +48,10 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
 
     Canonical network + reference encoders: one fused tcgen05 kernel (encoding never touches HBM,
     ``netchunk`` is irrelevant).  Anything else: encoding kernel + generic layer kernels."""
+    if inputs.shape[0] == 0 and isinstance(fn, NeRF):      # empty ray batch: [0, S, 4|5] attached to the parameters, no kernel launch
+        link = sum((p.reshape(-1)[:0].sum() for p in fn.parameters() if p.requires_grad), torch.zeros((), device=inputs.device))
+        n_out = 4 if fn.use_viewdirs else fn.spec.output_ch
+        return torch.zeros(list(inputs.shape[:-1]) + [n_out], device=inputs.device) + link
     if _fusable(fn, embed_fn, embeddirs_fn, inputs, viewdirs):
         params = fn.hot_params()
         if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):      # inference: nothing to record
@@ -68,6 +72,9 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
 
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
     """NP/run_nerf.py:265-308 -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
+    if raw.shape[0] == 0:                     # empty ray batch: the reference's shapes, attached to `raw`, no kernel launch
+        total = raw[..., 3].sum(-1)
+        return raw[..., :3].sum(-2), total, total, raw[..., 3], total
     noise = None
     if raw_noise_std > 0.0:
         if pytest:      # fixed-RNG hook of the reference (:290-294): *uniform* numbers from numpy seed 0

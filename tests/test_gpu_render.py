@@ -294,3 +294,19 @@ def test_render_edge_sizes(cn, n):
         with torch.no_grad():
             one = cn.render(1, 1, None, chunk=4096, rays=(o[128:129].to(DEV), d[128:129].to(DEV)), **kw)
         assert torch.equal(one[0], rgb[128:129].detach()) and torch.equal(one[3], depth[128:129].detach())
+
+
+def test_stage_functions_accept_empty_batches(cn):
+    """raw2outputs / sample_pdf / run_network on zero rays return the reference's empty shapes."""
+    raw = torch.zeros(0, 64, 4, device=DEV, requires_grad=True)
+    z, d = torch.zeros(0, 64, device=DEV), torch.zeros(0, 3, device=DEV)
+    rgb, disp, acc, w, depth = cn.raw2outputs(raw, z, d, 0.0, True)
+    assert rgb.shape == (0, 3) and disp.shape == (0,) and acc.shape == (0,) and w.shape == (0, 64) and depth.shape == (0,)
+    assert cn.sample_pdf(torch.zeros(0, 63, device=DEV), torch.zeros(0, 62, device=DEV), 128, det=True).shape == (0, 128)
+    net = module_from_params(O.make_params(1, **ARCH), ARCH)
+    e, _ = cn.get_embedder(10, 0)
+    ed, _ = cn.get_embedder(4, 0)
+    out = cn.run_network(torch.zeros(0, 64, 3, device=DEV), torch.zeros(0, 3, device=DEV), net, e, ed)
+    assert out.shape == (0, 64, 4)
+    out.sum().backward()
+    assert all(float(p.grad.abs().max()) == 0.0 for p in net.hot_params())
