@@ -115,3 +115,22 @@ def test_full_size_training_step_is_deterministic_and_additive(cn, scene):
     for k in a:
         total = sum(p[k].double() for p in parts)
         assert rel_err(a[k], total) < 5e-5, k
+
+
+def test_config5_full_image_800x800_render_only(cn, scene):
+    """BASELINE config 5: an 800 x 800 novel view (640 000 rays) from a pose, chunk = 32768 as in the reference's render_path.
+    Properties: shapes, finiteness, acc in [0, 1], and a stripe of the image rendered alone equals the same rows of the full
+    render bit for bit (rays are independent; tiles and chunks fall differently in the two calls)."""
+    H = W = 800
+    K = [[1111.1, 0.0, 400.0], [0.0, 1111.1, 400.0], [0.0, 0.0, 1.0]]
+    c2w = torch.tensor([[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 4.0]], device=DEV)
+    with torch.no_grad():
+        rgb, disp, acc, depth, ex = cn.render(H, W, K, chunk=32768, c2w=c2w, **scene["kw"])
+        assert rgb.shape == (H, W, 3) and acc.shape == (H, W) and depth.shape == (H, W) and ex["rgb0"].shape == (H, W, 3)
+        assert torch.isfinite(rgb).all() and torch.isfinite(depth).all()
+        assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+        ro, rd = cn.get_rays(H, W, K, c2w)
+        rows = slice(391, 407)
+        s_rgb, _, s_acc, s_depth, _ = cn.render(H, W, K, chunk=5000, rays=(ro[rows].reshape(-1, 3), rd[rows].reshape(-1, 3)), **scene["kw"])
+    assert torch.equal(s_rgb.reshape(16, W, 3), rgb[rows]) and torch.equal(s_depth.reshape(16, W), depth[rows])
+    assert torch.equal(s_acc.reshape(16, W), acc[rows])
