@@ -34,9 +34,10 @@ constexpr size_t kDwPassFloats = (size_t)kNumSMs * 128 * 512;           // one p
 constexpr size_t kDbPassFloats = (size_t)kNumSMs * 2 * 256;             // one pass: [148][2][256] fp32
 constexpr size_t kWsDwPart = 256;                                       // [10 passes][148][128 x 512] fp32
 constexpr size_t kWsDbPart = kWsDwPart + kDwPasses * kDwPassFloats * 4; // [10 passes][148][2][256] fp32
-constexpr size_t kWsHeadPart = kWsDbPart + kDwPasses * kDbPassFloats * 4;   // [148][kHeadFloats] fp32
+constexpr int kHeadCtas = 2 * kNumSMs;                                  // the narrow-head kernel is a pure HBM stream: two CTAs per SM
+constexpr size_t kWsHeadPart = kWsDbPart + kDwPasses * kDbPassFloats * 4;   // [kHeadCtas][kHeadFloats] fp32
 constexpr int kHeadFloats = 384 + 256 + 4;                              // dW_rgb, dW_alpha, db_rgb(3)+db_alpha
-constexpr size_t kWsBytes = kWsHeadPart + (size_t)kNumSMs * kHeadFloats * 4 + 256;
+constexpr size_t kWsBytes = kWsHeadPart + (size_t)kHeadCtas * kHeadFloats * 4 + 256;
 
 constexpr float kGradTarget = 256.f;                                    // max|d_raw| is scaled to [128, 256]
 
@@ -744,9 +745,10 @@ extern "C" int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_p
     BwdCtx c;
     int rc = bwd_ctx(acts, nullptr, n_points, workspace, stream, &c);
     if (rc != CNERF_OK) return rc;
-    mlp_heads_grad_kernel<<<c.grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
+    const int head_grid = c.tiles < kHeadCtas ? c.tiles : kHeadCtas;
+    mlp_heads_grad_kernel<<<head_grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
     CNERF_LAUNCH_CHECK("mlp_heads_grad_kernel");
-    heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, c.st>>>(c.head_part, c.grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
+    heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, c.st>>>(c.head_part, head_grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
     CNERF_LAUNCH_CHECK("heads_reduce_kernel");
     return CNERF_OK;
 }
