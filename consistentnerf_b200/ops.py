@@ -501,6 +501,7 @@ class CompositeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z, rays_d, noise, white_bkgd: bool):
         _need_cuda(raw, "raw2outputs")
+        ctx.set_materialize_grads(False)          # unused outputs (disp, acc, weights ...) arrive as None, not as zero-filled tensors
         raw_c, z_c = _f32c(raw.detach()), _f32c(z.detach())
         n, S = z_c.shape
         d = rays_d.detach()
@@ -589,6 +590,7 @@ class MaskedMSEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, mask, divisor: float, coef: float, n_ref: float, use_unmasked: bool):
         _need_cuda(pred, "masked_mse")
+        ctx.set_materialize_grads(False)          # the statistics output carries no gradient: no zero tensor is made for it
         p = _f32c(pred.detach())
         p2 = p.reshape(p.shape[0], -1)
         t2 = _f32c(target.detach()).reshape(p2.shape)
@@ -607,6 +609,8 @@ class MaskedMSEFn(torch.autograd.Function):
         p2, t2, m, out = ctx.saved_tensors
         divisor, coef, n_ref, use_unmasked, shape = ctx.cfg
         n, C = p2.shape
+        if g_loss is None:                        # only the statistics were used downstream
+            return None, None, None, None, None, None, None
         g = _f32c(g_loss).reshape(1)
         d = torch.empty_like(p2)
         call("cnerf_masked_mse_bwd", ptr(p2), ptr(t2), ptr(m), n, C, divisor, coef, n_ref, use_unmasked, ptr(out), ptr(g),
