@@ -184,6 +184,10 @@ def run_b200(args):
     from consistentnerf_b200.distributed import FlatGrads
 
     train = args.mode == "train"
+    if args.grad_precision:
+        cn.ops.set_grad_precision(args.grad_precision)
+    grad_mode = cn.ops.grad_precision()
+    dw_bytes_per_point = DW_BYTES_PER_POINT if cn.ops.GRAD_PRECISIONS[grad_mode][1] == 3 else DW_BYTES_PER_POINT // 2
     coarse, fine = make_nets(dev)
     embed_fn, _ = cn.get_embedder(10, 0)
     embeddirs_fn, _ = cn.get_embedder(4, 0)
@@ -293,7 +297,7 @@ def run_b200(args):
     achieved = kernels[top]["achieved_tflops"]
     if "cnerf_mlp_bwd_weights" in kernels:      # HBM-bound stage (ncu: 73 % DRAM throughput, 30 % tensor pipe): report both rooflines
         k = kernels["cnerf_mlp_bwd_weights"]
-        gbs = DW_BYTES_PER_POINT * POINTS_PER_RAY * N_RAYS / (kern_ms["cnerf_mlp_bwd_weights"] * 1e-3) / 1e9
+        gbs = dw_bytes_per_point * POINTS_PER_RAY * N_RAYS / (kern_ms["cnerf_mlp_bwd_weights"] * 1e-3) / 1e9
         k["achieved_gbs"], k["hbm_frac"] = gbs, gbs / hbm_peak
     mlp_flops_step = FLOP_PER_POINT * POINTS_PER_RAY * N_RAYS * (3 if train else 1)
     step_tf = mlp_flops_step / (ms_step * 1e-3) / 1e12
@@ -312,7 +316,7 @@ def run_b200(args):
         "config": {"workload": f"A: {N_RAYS} rays/GPU x ({N_SAMPLES} coarse + {N_IMPORTANCE} fine), viewdirs, 8x256 coarse+fine MLPs, "
                                + ("train step: render + masked rgb/depth losses + backward + grad all-reduce + Adam" if train
                                   else "render-only, no_grad, perturb=0"),
-                   "mode": args.mode, "rays_per_gpu": N_RAYS, "parallelism": f"ray-tile dp{world}",
+                   "mode": args.mode, "grad_precision": grad_mode, "rays_per_gpu": N_RAYS, "parallelism": f"ray-tile dp{world}",
                    "l2": "256 MiB memset between timed iterations (value); e2e streams fresh host batches"},
         "e2e": {"value": e2e_rays, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -394,6 +398,8 @@ def main():
     ap.add_argument("--mode", choices=["train", "render"], default="train")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-precision", choices=["split", "dw16", "fp16"], default=None,
+                    help="precision of the tensor-core backward (consistentnerf_b200.ops.GRAD_PRECISIONS); default: the package default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -38,22 +38,13 @@ SIGNATURES = {
     "cnerf_weights_refresh": (_I, [_P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_mlp_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "cnerf_mlp_acts_bytes": (c_int64, [c_int64]),
-    "cnerf_mlp_fwd_train": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "cnerf_mlp_fwd_train": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "cnerf_mlp_grads_bytes": (c_int64, [c_int64]),
     "cnerf_mlp_bwd_workspace_bytes": (c_int64, []),
-    "cnerf_mlp_bwd": (_I, [_P, _P, _P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
-    "cnerf_mlp_bwd_data": (_I, [_P, _P, _P, _P, _I, _P, _P]),
-    "cnerf_mlp_bwd_weights": (_I, [_P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _I, _P, _P]),
-    "cnerf_mlp_bwd_heads": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P, _P]),
-    "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
-    "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
-    "cnerf_debug_profile4": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
-    "cnerf_debug_profile_chain": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
-    "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
-    "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
-    "cnerf_umma_selftest_pair": (_I, [_P, _P, _I, _I, _P, _P]),
-    "cnerf_debug_pair_layout": (_I, [_P, _P, _I, _I, _P, _P]),
-    "cnerf_debug_umma_rate_pair": (_I, [_I, _I, _I, _P, _P, _P]),
+    "cnerf_mlp_bwd": (_I, [_P, _P, _P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "cnerf_mlp_bwd_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "cnerf_mlp_bwd_weights": (_I, [_P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _I, _I, _P, _P]),
+    "cnerf_mlp_bwd_heads": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P]),
     "cnerf_composite_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cnerf_composite_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_sample_pdf": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -61,8 +52,25 @@ SIGNATURES = {
     "cnerf_project_gather": (_I, [_P, _I, POINTER(c_float), POINTER(c_float), POINTER(c_float), _P, _I, _P, _I, _I,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnerf_hard_mask_pair": (_I, [_P, _P, _P, _I, POINTER(c_float), POINTER(c_float), _P, _I, _I, _F, _I, _I, _P, _P]),
-    "cnerf_masked_mse_fwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
+    "cnerf_masked_mse_fwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
     "cnerf_masked_mse_bwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
+}
+
+# include/cnerf_debug.h: self-tests, microbenchmarks, profiling hooks -- not part of the drop-in boundary
+DEBUG_SIGNATURES = {
+    "cnerf_umma_selftest": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_debug_mlp_fwd_terms": (_I, [_P, _P, _P, _I, _I, _P, _I, _P]),
+    "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_profile_chain": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
+}
+# only in builds made with `python -m consistentnerf_b200.build --experiments` (csrc/experiments/)
+EXPERIMENT_SIGNATURES = {
+    "cnerf_umma_selftest_pair": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_debug_profile4": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_pair_layout": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cnerf_debug_umma_rate_pair": (_I, [_I, _I, _I, _P, _P, _P]),
 }
 
 _dll = None
@@ -78,10 +86,15 @@ def load() -> ctypes.CDLL:
             f"{LIB_PATH} not found: the CUDA library is required (no fallback path exists). "
             "Build it with `python -m consistentnerf_b200.build`.")
     dll = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in {**SIGNATURES, **DEBUG_SIGNATURES}.items():
         fn = getattr(dll, name)      # AttributeError here == missing export
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in EXPERIMENT_SIGNATURES.items():
+        if hasattr(dll, name):
+            fn = getattr(dll, name)
+            fn.restype = res
+            fn.argtypes = args
     _dll = dll
     return dll
 

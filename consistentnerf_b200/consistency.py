@@ -92,12 +92,17 @@ def build_hard_masks(rays_o_views: Sequence[torch.Tensor], rays_d_views: Sequenc
     return masks
 
 
-def masked_img_loss(rgb, target, mask, hardmask_coef: float, n_rand: Optional[int] = None, return_stats: bool = False):
+def masked_img_loss(rgb, target, mask, hardmask_coef: float, n_rand: Optional[int] = None, return_stats: bool = False,
+                    global_counts=None):
     """img2mse(rgb[mask==1], target[mask==1]) + [mask.sum() != N_rand] * coef * img2mse(... mask==0).
+    ``global_counts`` (distributed.global_mask_counts): the rows are one rank's shard of a global batch; the means run over the
+    global batch and the returned value is this rank's additive share of the single-GPU loss (``n_rand`` = global N_rand).
     ``return_stats``: also the kernel's 5 device scalars [loss, #mask==1, #mask==0, plain img2mse over all rows, sum(mask)] --
     the quantities train() logs every step (NP/run_nerf_view.py:1908-1924) come out of the same launch, see ``loss_scalars``."""
     n_ref = float(rgb.shape[0] if n_rand is None else n_rand)
-    loss, stats = ops.MaskedMSEFn.apply(rgb, target, mask, 1.0, float(hardmask_coef), n_ref, True)
+    if global_counts is not None and n_rand is None:
+        raise ValueError("masked_img_loss: pass the GLOBAL n_rand together with global_counts")
+    loss, stats = ops.MaskedMSEFn.apply(rgb, target, mask, 1.0, float(hardmask_coef), n_ref, True, global_counts)
     return (loss, stats) if return_stats else loss
 
 
@@ -111,9 +116,10 @@ def loss_scalars(stats: torch.Tensor, prefix: str = "") -> dict:
 
 
 def masked_depth_loss(depth_pred, depth_prior, mask, far: float, hardmask_coef: float = 0.0,
-                      n_rand: Optional[int] = None, include_unmasked: bool = False, return_stats: bool = False):
+                      n_rand: Optional[int] = None, include_unmasked: bool = False, return_stats: bool = False,
+                      global_counts=None):
     """img2mse(d[mask==1]/far, prior[mask==1]/far) (+ coef * unmasked term in the cal_correspondance recipe)."""
     n_ref = float(depth_pred.shape[0] if n_rand is None else n_rand)
     loss, stats = ops.MaskedMSEFn.apply(depth_pred.reshape(-1, 1), depth_prior.reshape(-1, 1), mask, float(far),
-                                        float(hardmask_coef), n_ref, bool(include_unmasked))
+                                        float(hardmask_coef), n_ref, bool(include_unmasked), global_counts)
     return (loss, stats) if return_stats else loss

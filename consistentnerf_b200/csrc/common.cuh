@@ -6,7 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 
-#include "../../include/cnerf.h"
+#include "../../include/cnerf_debug.h"
 
 namespace cnerf {
 

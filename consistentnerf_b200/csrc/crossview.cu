@@ -156,17 +156,23 @@ masked_mse_partial_kernel(const float* __restrict__ pred, const float* __restric
 }
 
 __global__ void masked_mse_final_kernel(const double* __restrict__ part, int nblocks, int n, int C, float coef,
-                                        float n_ref, int use_unmasked, float* __restrict__ out) {
+                                        float n_ref, int use_unmasked, const float* __restrict__ global_counts,
+                                        float* __restrict__ out) {
     if (threadIdx.x != 0) return;
     double v[6] = {0, 0, 0, 0, 0, 0};
     for (int b = 0; b < nblocks; ++b)
         for (int k = 0; k < 6; ++k) v[k] += part[(size_t)b * 6 + k];
+    double nrows = (double)n;
+    if (global_counts) {      // this rank's share of a loss whose means run over the GLOBAL batch: denominators from all ranks
+        v[2] = (double)global_counts[0]; v[3] = (double)global_counts[1]; v[5] = (double)global_counts[2];
+        nrows = (double)global_counts[3];
+    }
     double loss = v[0] / (v[2] * C);
     if (use_unmasked && v[5] != (double)n_ref) loss += (double)coef * (v[1] / (v[3] * C));
     out[0] = (float)loss;
     out[1] = (float)v[2];
     out[2] = (float)v[3];
-    out[3] = (float)(v[4] / ((double)n * C));
+    out[3] = (float)(v[4] / (nrows * C));
     out[4] = (float)v[5];
 }
 
@@ -231,15 +237,15 @@ extern "C" int cnerf_hard_mask_pair(const float* rays_o, const float* rays_d, co
 }
 
 extern "C" int cnerf_masked_mse_fwd(const float* pred, const float* target, const float* mask, int n, int C,
-                                    float divisor, float coef, float n_ref, int use_unmasked, float* out,
-                                    void* workspace, void* stream) {
+                                    float divisor, float coef, float n_ref, int use_unmasked, const float* global_counts,
+                                    float* out, void* workspace, void* stream) {
     CNERF_REQUIRE(pred && target && out && workspace, "cnerf_masked_mse_fwd: null pointer");
     CNERF_REQUIRE(n >= 0 && C >= 1, "cnerf_masked_mse_fwd: bad sizes");
     int blocks = n == 0 ? 1 : (ceil_div(n, kLossThreads) < kLossBlocks ? ceil_div(n, kLossThreads) : kLossBlocks);
     double* part = reinterpret_cast<double*>(workspace);
     masked_mse_partial_kernel<<<blocks, kLossThreads, 0, as_stream(stream)>>>(pred, target, mask, n, C, divisor, part);
     CNERF_LAUNCH_CHECK("masked_mse_partial_kernel");
-    masked_mse_final_kernel<<<1, 32, 0, as_stream(stream)>>>(part, blocks, n, C, coef, n_ref, use_unmasked, out);
+    masked_mse_final_kernel<<<1, 32, 0, as_stream(stream)>>>(part, blocks, n, C, coef, n_ref, use_unmasked, global_counts, out);
     CNERF_LAUNCH_CHECK("masked_mse_final_kernel");
     return CNERF_OK;
 }

@@ -105,13 +105,20 @@ __device__ __forceinline__ void tmem_ld8g(uint32_t taddr, float* v) {
                  : "r"(taddr) : "memory");
 }
 // one k-group of G: hi/lo words into the SMEM operand tile (the MMA warp streams finished k-blocks to the record)
+template <bool kLo>
 __device__ __forceinline__ void emit_g(uint32_t hi_base, uint32_t lo_base, uint32_t row, uint32_t kg, const float* v) {
     uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
     const uint32_t off = kg * kLBO + row * 16;
-    st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
-    st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
+    if (kLo) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+        st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+        st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { __half2 t = __floats2half2_rn(v[2 * i], v[2 * i + 1]); h[i] = *reinterpret_cast<uint32_t*>(&t); }
+        st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+    }
 }
 
 __device__ unsigned long long g_profc[16];
@@ -119,7 +126,9 @@ __device__ unsigned long long g_profc[16];
 #define PROFC_ADD(var) do { if (kProf) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
 
 // kProf: instrumented instantiation for the phase profile (cnerf_debug_profile_chain); the production kernel carries none of it
-template <bool kProf>
+// kTerms: 3 = G W with the full hi/lo split (3 MMAs per MAC); 1 = fp16 operands, one MMA per MAC (only the hi halves of the
+//         weight blocks are fetched).  kSaveLo: the gradient record also carries the lo halves of G (three-term dW).
+template <bool kProf, int kTerms, bool kSaveLo>
 __global__ void __launch_bounds__(kC3Threads, 1)
 mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
                      const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
@@ -156,8 +165,9 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                 for (int b = 0; b < kC3NumBlocks; ++b, ++it) {
                     const uint32_t s = it % kC3Stages, ph = (it / kC3Stages) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * s, kBlockBytes);
-                    bulk_g2s_hint(sbase + kC3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kBlockBytes, bar_full + 8 * s, keep);
+                    constexpr uint32_t kFetch = kTerms == 1 ? kBlockHalfBytes : kBlockBytes;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, kFetch);
+                    bulk_g2s_hint(sbase + kC3Ring + s * kBlockBytes, wstream + (size_t)b * kBlockBytes, kFetch, bar_full + 8 * s, keep);
                 }
         }
     } else if (warp == 17) {
@@ -177,7 +187,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                 uint8_t* slot = grec + g_slot(layer);
                 const size_t lo_off = layer == 9 ? 32768 : 65536;
                 bulk_s2g_hint(slot + (size_t)kb * 8192, sbase + kC3ActHi + kb * 8192, 8192, stream_pol);
-                bulk_s2g_hint(slot + lo_off + (size_t)kb * 8192, sbase + kC3ActLo + kb * 8192, 8192, stream_pol);
+                if (kSaveLo) bulk_s2g_hint(slot + lo_off + (size_t)kb * 8192, sbase + kC3ActLo + kb * 8192, 8192, stream_pol);
                 bulk_commit();
             };
 #pragma unroll 1
@@ -201,8 +211,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                         const uint64_t bh = b256 + (uint64_t)(s * (kBlockBytes >> 4)), bl = bh + (kBlockHalfBytes >> 4);
                         const uint64_t ah = act_hi + (uint64_t)(j * kStep), al = act_lo + (uint64_t)(j * kStep);
                         umma_f16(d, ah, bh, idesc, j == 0 ? 0u : 1u);
-                        umma_f16(d, ah, bl, idesc, 1u);
-                        umma_f16(d, al, bh, idesc, 1u);
+                        if (kTerms == 3) { umma_f16(d, ah, bl, idesc, 1u); umma_f16(d, al, bh, idesc, 1u); }
                         umma_commit(bar_empty + 8 * s);
                         if (j + 1 == nb) {
                             bulk_wait_read0();                  // the epilogue overwrites the operand tile once it sees this step done
@@ -262,7 +271,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
                                  dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
                     v[j] = ((mbits >> j) & 1u) ? clamp_h(gsum) : 0.f;
                 }
-                emit_g(ah, al, row, kg, v);
+                emit_g<kTerms == 3 || kSaveLo>(ah, al, row, kg, v);
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
@@ -303,7 +312,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
 #pragma unroll
                             for (int j = 0; j < 8; ++j) w[j] = clamp_h(w[j]);
                         }
-                        emit_g(ah, al, row, kg, w);
+                        emit_g<kTerms == 3 || kSaveLo>(ah, al, row, kg, w);
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
@@ -335,10 +344,12 @@ struct DwPass {
     DwSrc a[2];            // G sources in the gradient record (kgroups 32 -> two 128-row halves, 16 -> one)
     DwSrc x[2];            // X sources in the activation record (N = 8 * kgroups)
     int db_mask;           // bit i: sum bias gradient of a[i]
+    int terms;             // 3: G and X as fp16 hi + lo, three MMAs per MAC; 1: hi halves only (fp16 operands), one MMA per MAC
 };
 
-constexpr int kDwStages = 3;
-constexpr uint32_t kDwStageBytes = 73728;                     // 72 KB: two 256-wide G quarters + the 64-wide encoding
+constexpr int kDwStages = 3;                                  // three-term mode; the fp16 mode runs 2 x kDwStages half-size stages
+constexpr int kDwMaxStages = 2 * kDwStages;
+constexpr uint32_t kDwStageBytes = 73728;                     // 72 KB: two 256-wide G quarters + the 64-wide encoding (hi + lo)
 constexpr uint32_t kDwBars = kDwStages * kDwStageBytes;       // 221184
 constexpr uint32_t kDwSmem = kDwBars + 128;
 constexpr int kDwThreads = 320;                               // 8 reduction/epilogue warps, loader warp, MMA warp
@@ -356,8 +367,10 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwStages, bar_acc = bar_empty + 8 * kDwStages;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kDwBars + 96);
+    const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwMaxStages, bar_acc = bar_empty + 8 * kDwMaxStages;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kDwBars + 112);
+    const uint32_t nhalf = P.terms == 1 ? 1u : 2u;                          // operand halves per source in a stage
+    const uint32_t n_stages = P.terms == 1 ? kDwMaxStages : kDwStages, stage_stride = P.terms == 1 ? kDwStageBytes / 2 : kDwStageBytes;
 
     // contiguous tile range of this CTA
     const int per = num_tiles / gridDim.x, rem = num_tiles % gridDim.x;
@@ -366,16 +379,16 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     // stage map: A sources then X sources, each [hi kgroups*512 | lo kgroups*512]
     uint32_t a_off[2], x_off[2], off = 0;
-    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += 2 * P.a[i].kgroups * kQuarter; }
-    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += 2 * P.x[j].kgroups * kQuarter; }
+    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += nhalf * P.a[i].kgroups * kQuarter; }
+    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += nhalf * P.x[j].kgroups * kQuarter; }
     const uint32_t stage_bytes = off;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kDwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 9); }
+        for (int s = 0; s < kDwMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 9); }
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(sbase + kDwBars + 96, 512);
+    if (warp == 9) tmem_alloc(sbase + kDwBars + 112, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -386,10 +399,10 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) {
             for (int it = 0; it < n_stage_iters; ++it) {
                 const int tile = t0 + (it >> 2), q = it & 3;
-                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
-                const uint32_t dst0 = sbase + s * kDwStageBytes;
+                const uint32_t dst0 = sbase + s * stage_stride;
                 for (int i = 0; i < P.n_a + P.n_x; ++i) {
                     const bool is_a = i < P.n_a;
                     const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
@@ -397,7 +410,7 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const uint32_t row0 = (uint32_t)tile * (uint32_t)((is_a ? kGTileBytes : kTileBytes) / 2048) + src.slot_off / 2048;
                     const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
                     tma_load_2d(d, map, q * 256, row0, bar_full + 8 * s);                 // box rows = 2*kgroups or kgroups
-                    if (src.lo_off != src.kgroups * 2048)
+                    if (nhalf == 2 && src.lo_off != src.kgroups * 2048)
                         tma_load_2d(d + src.kgroups * kQuarter, map, q * 256, row0 + src.lo_off / 2048, bar_full + 8 * s);
                 }
             }
@@ -406,10 +419,10 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===== MMA issuer =====
         if (lane == 0) {
             for (int it = 0; it < n_stage_iters; ++it) {
-                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t st = sbase + s * kDwStageBytes;
+                const uint32_t st = sbase + s * stage_stride;
 #pragma unroll 1
                 for (uint32_t ks = 0; ks < 2; ++ks) {
                     uint32_t col = 0;
@@ -424,8 +437,7 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                 const uint64_t xh = smem_desc_any(x_hi, 128, kQuarter), xl = smem_desc_any(x_hi + P.x[j].kgroups * kQuarter, 128, kQuarter);
                                 const uint32_t idesc = instr_desc_mn(128, N);
                                 umma_f16(tmem + col, ah, xh, idesc, (it == 0 && ks == 0) ? 0u : 1u);
-                                umma_f16(tmem + col, ah, xl, idesc, 1u);
-                                umma_f16(tmem + col, al, xh, idesc, 1u);
+                                if (nhalf == 2) { umma_f16(tmem + col, ah, xl, idesc, 1u); umma_f16(tmem + col, al, xh, idesc, 1u); }
                                 col += N;
                             }
                         }
@@ -443,9 +455,9 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
         for (int it = 0; it < n_stage_iters; ++it) {
-            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+            const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
             mbar_wait(bar_full + 8 * s, ph);
-            const uint32_t st = sbase + s * kDwStageBytes;
+            const uint32_t st = sbase + s * stage_stride;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (i < P.n_a && ((P.db_mask >> i) & 1)) {
@@ -455,9 +467,10 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if (g < per_warp) {
                             const uint32_t kg = warp * per_warp + g;
                             const uint32_t addr = st + a_off[i] + kg * kQuarter + lane * 16;
-                            uint4 hi, lo;
+                            uint4 hi, lo = make_uint4(0u, 0u, 0u, 0u);
                             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(addr));
-                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * kQuarter));
+                            if (nhalf == 2)
+                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * kQuarter));
                             const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -553,9 +566,11 @@ __global__ void db_reduce_kernel(DbSegs S, const float* __restrict__ db_part, in
 // ------------------------------------------------------------------------------------
 // 3. narrow heads in fp32: dW_rgb[ch][n] = sum d_rgb[p][ch] hv[p][n], dW_alpha[k] = sum d_sigma[p] h7[p][k]
 // ------------------------------------------------------------------------------------
+template <bool kLo>
 __device__ __forceinline__ void load_hilo8(const uint8_t* hi_ptr, size_t lo_off, float* out) {
     uint4 hi = __ldg(reinterpret_cast<const uint4*>(hi_ptr));
-    uint4 lo = __ldg(reinterpret_cast<const uint4*>(hi_ptr + lo_off));
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u);
+    if (kLo) lo = __ldg(reinterpret_cast<const uint4*>(hi_ptr + lo_off));
     const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -565,6 +580,7 @@ __device__ __forceinline__ void load_hilo8(const uint8_t* hi_ptr, size_t lo_off,
     }
 }
 
+template <bool kLo>      // kLo: the activation record carries the lo halves
 __global__ void __launch_bounds__(256)
 mlp_heads_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict__ acts, int n_points, float* __restrict__ part) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -583,7 +599,7 @@ mlp_heads_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict
             float v[8];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                     // hv: 16 k-groups, two per warp
-                load_hilo8(rec + kSlotHV + (size_t)(warp * 2 + g) * 2048 + row * 16, 32768, v);
+                load_hilo8<kLo>(rec + kSlotHV + (size_t)(warp * 2 + g) * 2048 + row * 16, 32768, v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     rgb[0][g * 8 + e] = fmaf(dr.x, v[e], rgb[0][g * 8 + e]);
@@ -593,7 +609,7 @@ mlp_heads_grad_kernel(const float* __restrict__ d_raw, const uint8_t* __restrict
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {                     // h7: 32 k-groups, four per warp
-                load_hilo8(rec + kSlotH0 + 7 * 131072 + (size_t)(warp * 4 + g) * 2048 + row * 16, 65536, v);
+                load_hilo8<kLo>(rec + kSlotH0 + 7 * 131072 + (size_t)(warp * 4 + g) * 2048 + row * 16, 65536, v);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) al[g * 8 + e] = fmaf(dr.w, v[e], al[g * 8 + e]);
             }
@@ -683,8 +699,11 @@ struct BwdCtx {
 int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, void* stream, BwdCtx* c) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
         attr_set = true;
@@ -717,9 +736,17 @@ extern "C" int cnerf_debug_profile_chain(int enable, unsigned long long* out16) 
 }
 
 // Stage 1: gradient scale + data-gradient chain -> grads_rec (G tiles of every layer).
+static int check_terms(const char* who, int chain_terms, int dw_terms) {
+    CNERF_REQUIRE(chain_terms == 1 || chain_terms == 3, "%s: chain_terms must be 1 (fp16 operands) or 3 (hi/lo split)", who);
+    CNERF_REQUIRE(dw_terms == 1 || dw_terms == 3, "%s: dw_terms must be 1 (fp16 operands) or 3 (hi/lo split)", who);
+    CNERF_REQUIRE(!(chain_terms == 1 && dw_terms == 3), "%s: a one-term chain does not produce the lo halves a three-term dW reads", who);
+    return CNERF_OK;
+}
+
 extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec,
-                                  int n_points, void* workspace, void* stream) {
+                                  int n_points, int chain_terms, int dw_terms, void* workspace, void* stream) {
     CNERF_REQUIRE(w && w->packed && w->stream_bwd3, "cnerf_mlp_bwd_data: weights handle not packed");
+    if (int rc = check_terms("cnerf_mlp_bwd_data", chain_terms, dw_terms)) return rc;
     CNERF_REQUIRE(d_raw && acts && grads_rec && workspace, "cnerf_mlp_bwd_data: null pointer");
     CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_data: negative n_points");
     if (n_points == 0) return CNERF_OK;
@@ -730,15 +757,20 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(amax)");
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
-    if (g_profc_host) mlp_bwd_data3_kernel<true><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
-    else mlp_bwd_data3_kernel<false><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+#define CNERF_CHAIN(P, T, L) mlp_bwd_data3_kernel<P, T, L><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g)
+    if (chain_terms == 1) { if (g_profc_host) CNERF_CHAIN(true, 1, false); else CNERF_CHAIN(false, 1, false); }
+    else if (dw_terms == 1) CNERF_CHAIN(false, 3, false);
+    else if (g_profc_host) CNERF_CHAIN(true, 3, true);
+    else CNERF_CHAIN(false, 3, true);
+#undef CNERF_CHAIN
     CNERF_LAUNCH_CHECK("mlp_bwd_data3_kernel");
     return CNERF_OK;
 }
 
 // Stage 3: the two narrow heads (needs only d_raw and the activation record).
 extern "C" int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, float* d_alpha_w, float* d_alpha_b,
-                                   float* d_rgb_w, float* d_rgb_b, int accumulate, void* workspace, void* stream) {
+                                   float* d_rgb_w, float* d_rgb_b, int accumulate, int dw_terms, void* workspace, void* stream) {
+    if (int rc0 = check_terms("cnerf_mlp_bwd_heads", 3, dw_terms)) return rc0;
     CNERF_REQUIRE(d_raw && acts && workspace && d_alpha_w && d_alpha_b && d_rgb_w && d_rgb_b, "cnerf_mlp_bwd_heads: null pointer");
     CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_heads: negative n_points");
     if (n_points == 0) return CNERF_OK;
@@ -746,7 +778,8 @@ extern "C" int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_p
     int rc = bwd_ctx(acts, nullptr, n_points, workspace, stream, &c);
     if (rc != CNERF_OK) return rc;
     const int head_grid = c.tiles < kHeadCtas ? c.tiles : kHeadCtas;
-    mlp_heads_grad_kernel<<<head_grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
+    if (dw_terms == 3) mlp_heads_grad_kernel<true><<<head_grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
+    else mlp_heads_grad_kernel<false><<<head_grid, 256, 0, c.st>>>(d_raw, c.a, n_points, c.head_part);
     CNERF_LAUNCH_CHECK("mlp_heads_grad_kernel");
     heads_reduce_kernel<<<ceil_div(kHeadFloats, 256), 256, 0, c.st>>>(c.head_part, head_grid, d_rgb_w, d_rgb_b, d_alpha_w, d_alpha_b, accumulate);
     CNERF_LAUNCH_CHECK("heads_reduce_kernel");
@@ -756,9 +789,10 @@ extern "C" int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_p
 // Stage 2: weight / bias gradients of the ten GEMM layers from grads_rec (after cnerf_mlp_bwd_data on the same workspace).
 extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, int n_points, float* const* d_pts_w,
                                      float* const* d_pts_b, float* d_feature_w, float* d_feature_b, float* d_views_w,
-                                     float* d_views_b, int accumulate, void* workspace, void* stream) {
+                                     float* d_views_b, int accumulate, int dw_terms, void* workspace, void* stream) {
     CNERF_REQUIRE(acts && grads_rec && workspace && d_pts_w && d_pts_b && d_feature_w && d_feature_b && d_views_w && d_views_b,
                   "cnerf_mlp_bwd_weights: null pointer");
+    if (int rc0 = check_terms("cnerf_mlp_bwd_weights", 3, dw_terms)) return rc0;
     CNERF_REQUIRE(n_points >= 0, "cnerf_mlp_bwd_weights: negative n_points");
     for (int i = 0; i < 8; ++i) CNERF_REQUIRE(d_pts_w[i] && d_pts_b[i], "cnerf_mlp_bwd_weights: null pts_linears.%d gradient", i);
     if (n_points == 0) return CNERF_OK;
@@ -769,11 +803,12 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
     const int grid = c.grid, tiles = c.tiles;
     auto H = [](int l) { return (uint32_t)(kSlotH0 + (size_t)l * 131072); };
     const uint64_t a_rows = (uint64_t)tiles * (kTileBytes / 2048), g_rows = (uint64_t)tiles * (kGTileBytes / 2048);
-    auto box_rows = [](const DwSrc& s) { return s.lo_off == s.kgroups * 2048 ? 2 * s.kgroups : s.kgroups; };
+    auto box_rows = [dw_terms](const DwSrc& s) { return (dw_terms == 3 && s.lo_off == s.kgroups * 2048) ? 2 * s.kgroups : s.kgroups; };
     DwSegs all = {};
     DbSegs alldb = {};
     int pass = 0;
-    auto run_pass = [&](const DwPass& P, const DwSeg* segs, int nseg, float* db0, int n0, float* db1, int n1) -> int {
+    auto run_pass = [&](DwPass& P, const DwSeg* segs, int nseg, float* db0, int n0, float* db1, int n1) -> int {
+        P.terms = dw_terms;
         CUtensorMap ma, mx0, mx1;
         int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]));
         if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]));
@@ -820,10 +855,10 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
 extern "C" int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
                              float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
                              float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
-                             float* d_rgb_b, int accumulate, void* workspace, void* stream) {
-    int rc = cnerf_mlp_bwd_data(w, d_raw, acts, grads_rec, n_points, workspace, stream);
-    if (rc == CNERF_OK) rc = cnerf_mlp_bwd_heads(d_raw, acts, n_points, d_alpha_w, d_alpha_b, d_rgb_w, d_rgb_b, accumulate, workspace, stream);
+                             float* d_rgb_b, int accumulate, int chain_terms, int dw_terms, void* workspace, void* stream) {
+    int rc = cnerf_mlp_bwd_data(w, d_raw, acts, grads_rec, n_points, chain_terms, dw_terms, workspace, stream);
+    if (rc == CNERF_OK) rc = cnerf_mlp_bwd_heads(d_raw, acts, n_points, d_alpha_w, d_alpha_b, d_rgb_w, d_rgb_b, accumulate, dw_terms, workspace, stream);
     if (rc == CNERF_OK) rc = cnerf_mlp_bwd_weights(acts, grads_rec, n_points, d_pts_w, d_pts_b, d_feature_w, d_feature_b, d_views_w,
-                                                   d_views_b, accumulate, workspace, stream);
+                                                   d_views_b, accumulate, dw_terms, workspace, stream);
     return rc;
 }

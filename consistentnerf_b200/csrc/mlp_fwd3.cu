@@ -66,11 +66,15 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
 // ------------------------------------------------------------------------------------
 // (__maxnreg__(104/112) instead of the launch bound would avoid the few spills of the training variant, but 576 threads then
 // exceed the register file's allocation granularity: "too many resources requested for launch")
-template <bool kSave, bool kProf>
+// kSave: 0 inference; 1 training, the record carries the fp16 hi halves only (weight gradients in one fp16 MMA per MAC);
+//        2 training, hi + lo halves (weight gradients with the full three-term split).
+// kVar:  measurement variants only (cnerf_debug_mlp_fwd_terms): `terms` selects which of the three partial products are issued
+//        (bit 0 a_hi*w_hi, bit 1 a_hi*w_lo, bit 2 a_lo*w_hi); the production instantiations issue all three unconditionally.
+template <int kSave, bool kProf, bool kVar>
 __global__ void __launch_bounds__(k3Threads, 1)
 mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
-                  uint8_t* __restrict__ acts) {
+                  uint8_t* __restrict__ acts, int terms) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +129,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
             mbar_wait(bar_hv, tl_of_tile & 1);
             if (elect_one()) {
                 bulk_s2g_hint(rec_of_tile + kSlotHV, sbase + k3ActHi, 32768, stream_pol);
-                bulk_s2g_hint(rec_of_tile + kSlotHV + 32768, sbase + k3ActLo, 32768, stream_pol);
+                if (kSave == 2) bulk_s2g_hint(rec_of_tile + kSlotHV + 32768, sbase + k3ActLo, 32768, stream_pol);
                 bulk_commit();
             }
             __syncwarp();
@@ -133,7 +137,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             uint8_t* rec = kSave ? acts + (size_t)tile * kTileBytes : nullptr;
             { PROF_T0(); mbar_wait(bar_eready, (uint32_t)tl & 1); PROF_ADD(pw_e); }
-            if (kSave && elect_one()) { bulk_s2g_hint(rec + kSlotE, sbase + k3EmbHi, 32768, stream_pol); bulk_commit(); }
+            if (kSave && elect_one()) { bulk_s2g_hint(rec + kSlotE, sbase + k3EmbHi, kSave == 2 ? 32768 : 16384, stream_pol); bulk_commit(); }
             __syncwarp();
 #pragma unroll 1
             for (int layer = 0; layer < 9; ++layer) {
@@ -151,8 +155,8 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         { PROF_T0(); mbar_wait(bar_aready + 8 * kb, aph); PROF_ADD(pw_a); }
                         if (kSave && elect_one()) {           // this k-block of the A operand is final: stream it to the record
                             bulk_s2g_hint(slot + (size_t)kb * 8192, sbase + k3ActHi + kb * 8192, 8192, stream_pol);
-                            bulk_s2g_hint(slot + 65536 + (size_t)kb * 8192, sbase + k3ActLo + kb * 8192, 8192, stream_pol);
-                            if (layer == 6 && kb == 0) bulk_s2g_hint(rec + kSlotV, sbase + k3EmbHi, 32768, stream_pol);
+                            if (kSave == 2) bulk_s2g_hint(slot + 65536 + (size_t)kb * 8192, sbase + k3ActLo + kb * 8192, 8192, stream_pol);
+                            if (layer == 6 && kb == 0) bulk_s2g_hint(rec + kSlotV, sbase + k3EmbHi, kSave == 2 ? 32768 : 16384, stream_pol);
                             bulk_commit();
                         }
                         __syncwarp();
@@ -170,11 +174,11 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                             const uint64_t ah = (is_act ? act_hi + (uint64_t)(ja * kStep) : emb_hi + (uint64_t)(j * kStep));
                             const uint64_t al = (is_act ? act_lo + (uint64_t)(ja * kStep) : emb_lo + (uint64_t)(j * kStep));
                             umma_f16(d, ah, bh, idesc256, j == 0 ? 0u : 1u);
-                            umma_f16(d, ah, bl, idesc256, 1u);
-                            umma_f16(d, al, bh, idesc256, 1u);
+                            if (!kVar || (terms & 2)) umma_f16(d, ah, bl, idesc256, 1u);
+                            if (!kVar || (terms & 4)) umma_f16(d, al, bh, idesc256, 1u);
                         } else {                              // bias block: encoding columns 48-63 (column 63 == 1.0) x [0 .. 0, bias]
                             umma_f16(d, emb_hi + 3 * kStep, bh, idesc256, 1u);
-                            umma_f16(d, emb_hi + 3 * kStep, bl, idesc256, 1u);
+                            if (!kVar || (terms & 2)) umma_f16(d, emb_hi + 3 * kStep, bl, idesc256, 1u);
                         }
                         umma_commit(bar_empty + 8 * s);
                         if (j + 1 == nb) {
@@ -195,7 +199,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         { PROF_T0(); mbar_wait(bar_aready + 8 * j, aph); PROF_ADD(pw_a); }
                         if (kSave && elect_one()) {
                             bulk_s2g_hint(rec + kSlotF + (size_t)j * 8192, sbase + k3ActHi + j * 8192, 8192, stream_pol);
-                            bulk_s2g_hint(rec + kSlotF + 65536 + (size_t)j * 8192, sbase + k3ActLo + j * 8192, 8192, stream_pol);
+                            if (kSave == 2) bulk_s2g_hint(rec + kSlotF + 65536 + (size_t)j * 8192, sbase + k3ActLo + j * 8192, 8192, stream_pol);
                             bulk_commit();
                         }
                         __syncwarp();
@@ -208,11 +212,11 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         const uint64_t ah = j < 8 ? act_hi + (uint64_t)(j * 2 * kStep) : emb_hi;
                         const uint64_t al = j < 8 ? act_lo + (uint64_t)(j * 2 * kStep) : emb_lo;
                         umma_f16(d, ah, bh, idesc128, j == 0 ? 0u : 1u);
-                        umma_f16(d, ah, bl, idesc128, 1u);
-                        umma_f16(d, al, bh, idesc128, 1u);
+                        if (!kVar || (terms & 2)) umma_f16(d, ah, bl, idesc128, 1u);
+                        if (!kVar || (terms & 4)) umma_f16(d, al, bh, idesc128, 1u);
                         umma_f16(d, ah + kStep, bh + kStep, idesc128, 1u);
-                        umma_f16(d, ah + kStep, bl + kStep, idesc128, 1u);
-                        umma_f16(d, al + kStep, bh + kStep, idesc128, 1u);
+                        if (!kVar || (terms & 2)) umma_f16(d, ah + kStep, bl + kStep, idesc128, 1u);
+                        if (!kVar || (terms & 4)) umma_f16(d, al + kStep, bh + kStep, idesc128, 1u);
                         umma_commit(bar_empty + 8 * s);
                         if (j == 8) {
                             if (kSave) bulk_wait_read0();
@@ -405,28 +409,34 @@ int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st) {
 }
 int stream3_blocks() { return k3NumBlocks; }
 
-int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
-                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st) {
+template <int kSave, bool kProf, bool kVar>
+static int launch_fused3_inst(int grid, const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs,
+                              int n_points, int n_samples, int n_rays, float* raw, uint8_t* acts, int terms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused3_kernel<kSave, kProf, kVar>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3Smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused3_kernel)");
         attr_set = true;
     }
-    const int tiles = ceil_div(n_points, (int)kRows);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (g_prof3_host) {
-        if (acts) mlp_fused3_kernel<true, true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
-        else mlp_fused3_kernel<false, true><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
-    } else {
-        if (acts) mlp_fused3_kernel<true, false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
-        else mlp_fused3_kernel<false, false><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
-    }
+    mlp_fused3_kernel<kSave, kProf, kVar><<<grid, k3Threads, k3Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts, terms);
     CNERF_LAUNCH_CHECK("mlp_fused3_kernel");
     return CNERF_OK;
+}
+
+// record_lo: the training record also carries the lo halves (three-term weight gradients); terms: 7 = production, anything else
+// selects the measurement instantiation (inference only)
+int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, int record_lo, int terms, cudaStream_t st) {
+    const int tiles = ceil_div(n_points, (int)kRows);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+#define CNERF_F3(S, P, V) launch_fused3_inst<S, P, V>(grid, stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts, terms, st)
+    if (terms != 7) {
+        CNERF_REQUIRE(!acts, "mlp_fused3: the partial-product variants are inference only");
+        return CNERF_F3(0, false, true);
+    }
+    if (g_prof3_host) return acts ? (record_lo ? CNERF_F3(2, true, false) : CNERF_F3(1, true, false)) : CNERF_F3(0, true, false);
+    return acts ? (record_lo ? CNERF_F3(2, false, false) : CNERF_F3(1, false, false)) : CNERF_F3(0, false, false);
+#undef CNERF_F3
 }
 
 }  // namespace cnerf

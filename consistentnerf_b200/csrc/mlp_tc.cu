@@ -246,21 +246,26 @@ int bwd_stream3_blocks();                                                    // 
 int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st);
 int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st);                                // mlp_fwd3.cu
 int stream3_blocks();
-int pack_stream4(const RawParams& p, uint8_t* stream4, cudaStream_t st);                                // mlp_fwd4.cu
+#ifdef CNERF_EXPERIMENTS
+int pack_stream4(const RawParams& p, uint8_t* stream4, cudaStream_t st);                                // experiments/mlp_fwd4.cu
 size_t stream4_bytes();
 int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, cudaStream_t st);
+#endif
 int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
-                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, int record_lo, int terms, cudaStream_t st);
 }
 
-// Forward kernel selected once per process (CNERF_MLP_IMPL): default 3 = single-CTA N=256 kernel (mlp_fwd3.cu); 4 = CTA-pair
-// ping-pong experiment (mlp_fwd4.cu, inference only, correct but slower).  Only the streams in use are packed.
+// The product runs the single-CTA N=256 kernel (mlp_fwd3.cu).  A build with CNERF_EXPERIMENTS (python -m
+// consistentnerf_b200.build --experiments) also links the CTA-pair ping-pong experiment (experiments/mlp_fwd4.cu, inference
+// only, correct but 2.4x slower), selected once per process with CNERF_MLP_IMPL=4.
+#ifdef CNERF_EXPERIMENTS
 static int fwd_impl() {
     static int impl = 0;
     if (!impl) { const char* ev = getenv("CNERF_MLP_IMPL"); impl = (ev && ev[0] == '4') ? 4 : 3; }
     return impl;
 }
+#endif
 
 extern "C" int cnerf_weights_create(cnerf_weights** out) {
     CNERF_REQUIRE(out, "cnerf_weights_create: null out");
@@ -268,7 +273,9 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
     cudaGetDevice(&w->device);
     cudaError_t e = cudaMalloc(&w->stream3, (size_t)stream3_blocks() * kBlockBytes);
     if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd3, (size_t)bwd_stream3_blocks() * kBlockBytes);
+#ifdef CNERF_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&w->stream4, stream4_bytes());
+#endif
     if (e == cudaSuccess) e = cudaMalloc(&w->misc, kMiscFloats * sizeof(float));
     if (e != cudaSuccess) { cudaFree(w->stream3); cudaFree(w->stream_bwd3); cudaFree(w->stream4); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
     *out = w;
@@ -301,7 +308,9 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     pack_misc_kernel<<<ceil_div(kMiscFloats, 256), 256, 0, as_stream(stream)>>>(p, w->misc);
     CNERF_LAUNCH_CHECK("pack_misc_kernel");
     int rc = pack_stream3(p, w->stream3, as_stream(stream));
+#ifdef CNERF_EXPERIMENTS
     if (rc == CNERF_OK && fwd_impl() == 4) rc = pack_stream4(p, w->stream4, as_stream(stream));
+#endif
     if (rc == CNERF_OK) rc = pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream));
     if (rc != CNERF_OK) return rc;
     w->packed = true;
@@ -309,7 +318,7 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
 }
 
 static int launch_mlp(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                      float* raw, void* acts, void* stream, const char* who) {
+                      float* raw, void* acts, int record_lo, int terms, void* stream, const char* who) {
     CNERF_REQUIRE(w && w->packed, "%s: weights handle not packed (call cnerf_weights_refresh)", who);
     CNERF_REQUIRE(pts && viewdirs && raw, "%s: null pointer", who);
     CNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "%s: bad sizes", who);
@@ -317,14 +326,25 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     CNERF_REQUIRE(np64 < (int64_t)1 << 30, "%s: too many points in one call (%lld)", who, (long long)np64);
     if (np64 == 0) return CNERF_OK;
     int n_points = (int)np64;
-    if (fwd_impl() == 4 && !acts)      // the CTA-pair experiment is inference only; training runs the single-CTA kernel
+#ifdef CNERF_EXPERIMENTS
+    if (fwd_impl() == 4 && !acts && terms == 7)      // the CTA-pair experiment is inference only; training runs the single-CTA kernel
         return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, as_stream(stream));
-    return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
+#endif
+    return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, record_lo, terms,
+                         as_stream(stream));
 }
 
 extern "C" int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
                              float* raw, void* stream) {
-    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, stream, "cnerf_mlp_fwd");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, 7, stream, "cnerf_mlp_fwd");
+}
+
+// Measurement only (include/cnerf_debug.h): the forward with a subset of the three partial products of the fp16 hi/lo split
+// (bit 0 a_hi*w_hi, always issued; bit 1 a_hi*w_lo; bit 2 a_lo*w_hi) -- the error / speed table of DESIGN.md section 3.
+extern "C" int cnerf_debug_mlp_fwd_terms(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
+                                         int n_samples, float* raw, int terms, void* stream) {
+    CNERF_REQUIRE((terms & 1) && terms > 0 && terms < 8, "cnerf_debug_mlp_fwd_terms: terms must contain bit 0 and be < 8");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, terms == 7 ? 15 : terms, stream, "cnerf_debug_mlp_fwd_terms");
 }
 
 extern "C" int64_t cnerf_mlp_acts_bytes(int64_t n_points) {
@@ -332,9 +352,10 @@ extern "C" int64_t cnerf_mlp_acts_bytes(int64_t n_points) {
 }
 
 extern "C" int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
-                                   int n_samples, float* raw, void* acts, void* stream) {
+                                   int n_samples, float* raw, void* acts, int dw_terms, void* stream) {
     CNERF_REQUIRE(acts, "cnerf_mlp_fwd_train: null activation record buffer");
-    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, acts, stream, "cnerf_mlp_fwd_train");
+    CNERF_REQUIRE(dw_terms == 1 || dw_terms == 3, "cnerf_mlp_fwd_train: dw_terms must be 1 (fp16 record) or 3 (hi/lo record)");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, acts, dw_terms == 3, 7, stream, "cnerf_mlp_fwd_train");
 }
 
 extern "C" int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream) {

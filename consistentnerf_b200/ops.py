@@ -364,6 +364,11 @@ class PackedWeights:
         self._key = None
         self._finalizer = weakref.finalize(self, _lib.load().cnerf_weights_destroy, h)
 
+    def invalidate(self):
+        """Force a repack on the next use.  Needed after in-place edits made through ``.data`` (``p.data.mul_()``,
+        ``p.data.clamp_()`` ...): those bump a separate version counter, so the (data_ptr, _version) key below cannot see them."""
+        self._key = None
+
     def refresh(self, P: dict, force: bool = False):
         tensors = [P[f"pts_linears.{i}.weight"] for i in range(8)] + [P[f"pts_linears.{i}.bias"] for i in range(8)] + [
             P["feature_linear.weight"], P["feature_linear.bias"], P["alpha_linear.weight"], P["alpha_linear.bias"],
@@ -392,23 +397,48 @@ ACCUMULATE_IN_PLACE = os.environ.get("CNERF_GRAD_INPLACE", "1") != "0"      # se
 BWD_CHUNK_POINTS = 1 << 18      # activation recompute granularity of the CUDA-core backward pass
 MLP_BWD = os.environ.get("CNERF_MLP_BWD", "tc")      # "tc": tcgen05 backward, "simt": fp32 CUDA-core backward
 
+# Precision of the tensor-core backward (include/cnerf.h, K3b): name -> (chain_terms, dw_terms).
+#   "split"  every gradient GEMM with the forward's fp16 hi/lo three-term split (fp32-equivalent, gradients within 2e-5 of fp64)
+#   "dw16"   data-gradient chain split, weight-gradient operands (the G and X records) in fp16: half the record bytes, 1 MMA
+#   "fp16"   chain and weight gradients with fp16 operands, fp32 accumulation (what mixed-precision training does)
+# The FORWARD is always three-term (the rendered maps stay within 1e-4 of the fp32 reference in every mode).
+GRAD_PRECISIONS = {"split": (3, 3), "dw16": (3, 1), "fp16": (1, 1)}
+DEFAULT_GRAD_PRECISION = "split"
+_grad_precision = os.environ.get("CNERF_GRAD_PRECISION", DEFAULT_GRAD_PRECISION)
+if _grad_precision not in GRAD_PRECISIONS:
+    raise ValueError(f"CNERF_GRAD_PRECISION={_grad_precision!r}: expected one of {sorted(GRAD_PRECISIONS)}")
 
-def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor):
+
+def set_grad_precision(name: str) -> str:
+    """Select the backward precision for subsequent forward passes (returns the previous setting)."""
+    global _grad_precision
+    if name not in GRAD_PRECISIONS:
+        raise ValueError(f"grad precision {name!r}: expected one of {sorted(GRAD_PRECISIONS)}")
+    prev, _grad_precision = _grad_precision, name
+    return prev
+
+
+def grad_precision() -> str:
+    return _grad_precision
+
+
+def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor, dw_terms: int = 3):
     """Training-mode forward: raw [n,S,4] plus the activation record the tensor-core backward reads."""
     n, S = pts.shape[0], pts.shape[1]
     raw = torch.empty((n, S, 4), device=pts.device, dtype=_F32)
     nbytes = int(_lib.load().cnerf_mlp_acts_bytes(n * S))
     acts = torch.empty(nbytes, device=pts.device, dtype=torch.uint8)
-    call("cnerf_mlp_fwd_train", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ptr(acts), stream())
+    call("cnerf_mlp_fwd_train", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ptr(acts), int(dw_terms), stream())
     return raw, acts
 
 
 def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw: torch.Tensor, n_points: int,
-                       return_record: bool = False, accumulate_into: Optional[dict] = None):
+                       return_record: bool = False, accumulate_into: Optional[dict] = None, terms=(3, 3)):
     """Parameter gradients of the canonical network from d_raw [n_points,4] and the forward's activation record.
     ``accumulate_into`` (name -> contiguous fp32 tensor): add the gradients to these buffers (the parameters' .grad)
-    instead of returning fresh tensors."""
+    instead of returning fresh tensors.  ``terms`` = (chain_terms, dw_terms) as passed to the forward that wrote ``acts``."""
     dev = acts.device
+    chain_terms, dw_terms = int(terms[0]), int(terms[1])
     d_raw = _f32c(d_raw).reshape(n_points, 4)
     acc = int(accumulate_into is not None)
     grads = accumulate_into if acc else {k: torch.empty_like(v) for k, v in P.items()}
@@ -418,12 +448,12 @@ def fused_mlp_backward(packed: PackedWeights, P: dict, acts: torch.Tensor, d_raw
     pw = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.weight"].data_ptr() for i in range(8)])
     pb = (ctypes.c_void_p * 8)(*[grads[f"pts_linears.{i}.bias"].data_ptr() for i in range(8)])
     st = stream()
-    call("cnerf_mlp_bwd_data", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, ptr(ws), st)
+    call("cnerf_mlp_bwd_data", packed.handle, ptr(d_raw), ptr(acts), ptr(rec), n_points, chain_terms, dw_terms, ptr(ws), st)
     call("cnerf_mlp_bwd_heads", ptr(d_raw), ptr(acts), n_points, ptr(grads["alpha_linear.weight"]),
-         ptr(grads["alpha_linear.bias"]), ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), acc, ptr(ws), st)
+         ptr(grads["alpha_linear.bias"]), ptr(grads["rgb_linear.weight"]), ptr(grads["rgb_linear.bias"]), acc, dw_terms, ptr(ws), st)
     call("cnerf_mlp_bwd_weights", ptr(acts), ptr(rec), n_points, pw, pb, ptr(grads["feature_linear.weight"]),
          ptr(grads["feature_linear.bias"]), ptr(grads["views_linears.0.weight"]), ptr(grads["views_linears.0.bias"]),
-         acc, ptr(ws), st)
+         acc, dw_terms, ptr(ws), st)
     if return_record:
         return grads, rec
     return grads
@@ -444,7 +474,8 @@ class FusedMLPFn(torch.autograd.Function):
         ctx.params = params                      # the leaf tensors themselves: backward() may add straight into their .grad
         ctx.tc = MLP_BWD == "tc" and any(ctx.needs_input_grad[6:])
         if ctx.tc:
-            raw, acts = fused_mlp_forward_train(packed, pts_c, vd_c)
+            ctx.terms = GRAD_PRECISIONS[_grad_precision]
+            raw, acts = fused_mlp_forward_train(packed, pts_c, vd_c, ctx.terms[1])
             ctx.pack_key = packed._key
             ctx.save_for_backward(acts)
             ctx.n_points = pts_c.shape[0] * pts_c.shape[1]
@@ -462,16 +493,23 @@ class FusedMLPFn(torch.autograd.Function):
             packed = ctx.packed
             if packed._key != ctx.pack_key:
                 raise RuntimeError("parameters were modified in place between the forward and the backward pass")
-            # Every parameter already owns a gradient buffer (e.g. distributed.FlatGrads, or any step after the first with
-            # zero_grad(set_to_none=False)): the reduction kernels add into it -- what autograd's AccumulateGrad would do with
-            # 24 fresh tensors and 24 add kernels per network -- and autograd receives no gradient for these inputs.
+            # OPT-IN fast path (distributed.FlatGrads marks its parameters with ``_cnerf_accumulate_in_place``): the reduction
+            # kernels add straight into the parameters' .grad buffers -- what autograd's AccumulateGrad would do with 24 fresh
+            # tensors and 24 add kernels per network -- and autograd receives no gradient for these inputs.  Never inferred from
+            # ``p.grad is not None``: torch.autograd.grad, DDP reducers and post-accumulate-grad hooks rely on the returned
+            # gradients, so any parameter that is not marked (or carries hooks) takes the regular path below.
             leaves = ctx.params
             if ACCUMULATE_IN_PLACE and all(
-                    p.is_leaf and p.requires_grad and p.grad is not None and p.grad.dtype == _F32 and p.grad.is_contiguous()
-                    and p.grad.device == p.device and not p._backward_hooks for p in leaves):
-                fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points, accumulate_into={k: p.grad for k, p in zip(names, leaves)})
+                    getattr(p, "_cnerf_accumulate_in_place", False) and p.is_leaf and p.requires_grad and p.grad is not None
+                    and p.grad.dtype == _F32 and p.grad.is_contiguous() and p.grad.device == p.device
+                    and not p._backward_hooks and not getattr(p, "_post_accumulate_grad_hooks", None) for p in leaves):
+                fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points, accumulate_into={k: p.grad for k, p in zip(names, leaves)},
+                                   terms=ctx.terms)
+                hook = getattr(packed, "after_backward", None)      # distributed.FlatGrads.overlap_with_backward
+                if hook is not None:
+                    hook()
                 return (None,) * (6 + len(names))
-            grads = fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points)
+            grads = fused_mlp_backward(packed, P, acts, d_raw, ctx.n_points, terms=ctx.terms)
             return (None, None, None, None, None, None) + tuple(grads[k] for k in names)
         L, Lv = ctx.enc
         pts, viewdirs = ctx.saved_tensors
@@ -588,7 +626,7 @@ class MaskedMSEFn(torch.autograd.Function):
     """K7: masked / hard-mask-weighted MSE (NP/run_nerf_view.py:1645-1648,1737)."""
 
     @staticmethod
-    def forward(ctx, pred, target, mask, divisor: float, coef: float, n_ref: float, use_unmasked: bool):
+    def forward(ctx, pred, target, mask, divisor: float, coef: float, n_ref: float, use_unmasked: bool, global_counts=None):
         _need_cuda(pred, "masked_mse")
         ctx.set_materialize_grads(False)          # the statistics output carries no gradient: no zero tensor is made for it
         p = _f32c(pred.detach())
@@ -598,8 +636,11 @@ class MaskedMSEFn(torch.autograd.Function):
         n, C = p2.shape
         out = torch.empty(5, device=p.device, dtype=_F32)
         ws = _workspace(p.device, 8192)
+        gc = _f32c(global_counts.detach()) if global_counts is not None else None
+        if gc is not None and gc.numel() != 4:
+            raise ValueError("global_counts must hold 4 floats: #mask==1, #mask==0, sum(mask), #rows of the global batch")
         call("cnerf_masked_mse_fwd", ptr(p2), ptr(t2), ptr(m), n, C, float(divisor), float(coef), float(n_ref),
-             int(use_unmasked), ptr(out), ptr(ws), stream())
+             int(use_unmasked), ptr(gc), ptr(out), ptr(ws), stream())
         ctx.save_for_backward(p2, t2, m, out)
         ctx.cfg = (float(divisor), float(coef), float(n_ref), int(use_unmasked), pred.shape)
         return out[0], out
@@ -610,12 +651,12 @@ class MaskedMSEFn(torch.autograd.Function):
         divisor, coef, n_ref, use_unmasked, shape = ctx.cfg
         n, C = p2.shape
         if g_loss is None:                        # only the statistics were used downstream
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         g = _f32c(g_loss).reshape(1)
         d = torch.empty_like(p2)
         call("cnerf_masked_mse_bwd", ptr(p2), ptr(t2), ptr(m), n, C, divisor, coef, n_ref, use_unmasked, ptr(out), ptr(g),
              ptr(d), stream())
-        return d.reshape(shape), None, None, None, None, None, None
+        return d.reshape(shape), None, None, None, None, None, None, None
 
 
 def umma_selftest(a: torch.Tensor, b: torch.Tensor, a_in_tmem: bool = False) -> torch.Tensor:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CNERF_VERSION 100          /* 0.1.0 */
+#define CNERF_VERSION 200          /* 0.2.0: gradient-precision arguments on the K3b entry points */
 
 #define CNERF_OK        0
 #define CNERF_EINVAL    1          /* bad argument (shape, null pointer, unsupported size) */
@@ -108,9 +108,21 @@ int cnerf_linear_bwd_weight(const float* dy, int lddy, const float* y, int ldy, 
  * (run_network NP/run_nerf.py:37-52 + NeRF.forward).  Canonical architecture only:
  * D=8, W=256, skips=[4], use_viewdirs, multires=10, multires_views=4.
  *
- * Precision: every fp32 operand is split into two fp16 terms (hi + lo); each product is
- * evaluated as hi*hi + hi*lo + lo*hi on the tensor cores with fp32 accumulation in TMEM,
- * i.e. ~2^-21 relative per product -- fp32-equivalent, 3 MMAs per algorithmic MAC.
+ * Precision of the forward (inference and training): every fp32 operand is split into two
+ * fp16 terms (hi + lo); each product is evaluated as hi*hi + hi*lo + lo*hi on the tensor cores
+ * with fp32 accumulation in TMEM, i.e. ~2^-21 relative per product -- fp32-equivalent, 3 MMAs
+ * per algorithmic MAC.
+ *
+ * Precision of the backward (K3b) is chosen by the caller with two arguments:
+ *   chain_terms  3: the data-gradient chain G_{l-1} = (G_l W_l)[h>0] runs the same three-term split;
+ *                1: fp16 operands, ONE MMA per MAC (fp32 accumulation), only the hi halves of the
+ *                   weight blocks are fetched;
+ *   dw_terms     3: dW_l = G_l^T X_l from fp16 hi + lo records of G and X (4 B per element, 3 MMAs);
+ *                1: from the hi halves only (2 B per element -- half the record traffic of the
+ *                   forward, the chain and the weight-gradient stage -- and 1 MMA).
+ * The same dw_terms must be passed to cnerf_mlp_fwd_train and to every backward stage that reads
+ * its record; (chain_terms, dw_terms) = (1, 3) is rejected.  Rounding is to nearest (unbiased):
+ * per-element relative error 2^-11 in the one-term modes, averaged over the points of the batch.
  * ---------------------------------------------------------------------------------------- */
 typedef struct cnerf_weights cnerf_weights;   /* opaque: packed fp16 hi/lo weight stream of ONE NeRF */
 
@@ -126,11 +138,12 @@ int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w, const flo
 int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
                   int n_samples, float* raw, void* stream);
 /* Training-mode forward: same result as cnerf_mlp_fwd, and every layer's A operand (encodings, post-activation
- * outputs; fp16 hi/lo tiles) plus the ReLU sign bits are streamed into `acts` (cnerf_mlp_acts_bytes(n_rays*n_samples)
- * bytes, device: 1 345 536 per 128 points, opaque to the caller) for cnerf_mlp_bwd. */
+ * outputs; fp16 hi tiles, plus the lo tiles when dw_terms == 3) plus the ReLU sign bits are streamed into `acts`
+ * (cnerf_mlp_acts_bytes(n_rays*n_samples) bytes, device: 1 345 536 per 128 points, opaque to the caller) for
+ * cnerf_mlp_bwd.  With dw_terms == 1 the lo slots of the record are left untouched (never read). */
 int64_t cnerf_mlp_acts_bytes(int64_t n_points);
 int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                        float* raw, void* acts, void* stream);
+                        float* raw, void* acts, int dw_terms, void* stream);
 /* K3b backward on tensor cores (autograd of run_network w.r.t. the parameters; loss.backward() of
  * NP/run_nerf_view.py:1982 for this module).  d_raw [n_points,4]; `acts` from cnerf_mlp_fwd_train with the SAME packed
  * weights; `grads_rec` scratch of cnerf_mlp_grads_bytes(n_points) bytes; `workspace` of
@@ -141,25 +154,16 @@ int64_t cnerf_mlp_bwd_workspace_bytes(void);
 int cnerf_mlp_bwd(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
                   float* const* d_pts_w, float* const* d_pts_b, float* d_feature_w, float* d_feature_b,
                   float* d_alpha_w, float* d_alpha_b, float* d_views_w, float* d_views_b, float* d_rgb_w,
-                  float* d_rgb_b, int accumulate, void* workspace, void* stream);
+                  float* d_rgb_b, int accumulate, int chain_terms, int dw_terms, void* workspace, void* stream);
 /* The three stages of cnerf_mlp_bwd as separate calls (same buffers and workspace; cnerf_mlp_bwd_data first):
  * the data-gradient chain, the weight/bias gradients of the ten GEMM layers, the two narrow heads. */
 int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, const void* acts, void* grads_rec, int n_points,
-                       void* workspace, void* stream);
+                       int chain_terms, int dw_terms, void* workspace, void* stream);
 int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, int n_points, float* const* d_pts_w,
                           float* const* d_pts_b, float* d_feature_w, float* d_feature_b, float* d_views_w,
-                          float* d_views_b, int accumulate, void* workspace, void* stream);
+                          float* d_views_b, int accumulate, int dw_terms, void* workspace, void* stream);
 int cnerf_mlp_bwd_heads(const float* d_raw, const void* acts, int n_points, float* d_alpha_w, float* d_alpha_b,
-                        float* d_rgb_w, float* d_rgb_b, int accumulate, void* workspace, void* stream);
-/* Unit self-test of the tcgen05 building blocks: d[128,n] = a[128,k] b[n,k]^T with the same
- * fp16 hi/lo split, descriptors and TMEM read-back the fused kernel uses (k%16==0, n%16==0, n<=256). */
-int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream);
-/* Same product with the A operand staged in tensor memory (tcgen05.st + TS-mode MMA); k <= 256. */
-int cnerf_umma_selftest_ts(const float* a, const float* b, int n, int k, float* d, void* stream);
-/* CTA-pair variant (tcgen05 cta_group::2, one M=256 instruction stream for two SMs): d[256,n] = a[256,k] b[n,k]^T;
- * each CTA of the pair holds its 128 rows of a/d and n/2 rows of b.  n%32==0, n<=256, k<=128. */
-int cnerf_umma_selftest_pair(const float* a, const float* b, int n, int k, float* d, void* stream);
-
+                        float* d_rgb_w, float* d_rgb_b, int accumulate, int dw_terms, void* workspace, void* stream);
 /* ------------------------------------------------------------------------------------------
  * K4 alpha compositing -- raw2outputs NP/run_nerf.py:265-308 (depth_map as returned by
  * NP/run_nerf_view.py:392-439).
@@ -222,31 +226,18 @@ int cnerf_hard_mask_pair(const float* rays_o, const float* rays_d, const float* 
  * out[0] = mean_{mask==1}(e) + [use_unmasked && sum(mask) != n_ref] coef * mean_{mask==0}(e);
  * out[1] = #rows mask==1, out[2] = #rows mask==0, out[3] = plain mean over all rows (img2mse),
  * out[4] = sum(mask).  pred/target [n,C], mask [n] (NULL = all ones), out [5] floats.
+ * global_counts (device, 4 floats, or NULL): {#mask==1, #mask==0, sum(mask), #rows} of the GLOBAL batch when the rows
+ * are one rank's shard of it: the means are then taken over the global batch -- out[0] is this
+ * rank's additive share of the single-GPU loss (the ranks' shares sum to it, and so do the gradients), out[1], out[2],
+ * out[4] repeat the global counts, and n_ref must be the global reference count.
  * workspace: 8192 bytes of scratch (needs no initialisation).  Deterministic reduction order. */
 int cnerf_masked_mse_fwd(const float* pred, const float* target, const float* mask, int n, int C,
-                         float divisor, float coef, float n_ref, int use_unmasked, float* out,
-                         void* workspace, void* stream);
+                         float divisor, float coef, float n_ref, int use_unmasked, const float* global_counts,
+                         float* out, void* workspace, void* stream);
 /* d_pred [n,C] = g_loss[0] * d out[0] / d pred, using the counts in `out` from the forward. */
 int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* mask, int n, int C,
                          float divisor, float coef, float n_ref, int use_unmasked, const float* out,
                          const float* g_loss, float* d_pred, void* stream);
-
-/* Debug aid: enable/disable the in-kernel phase profile of the fused forward kernel (mlp_fwd3.cu) and read + clear its
- * 16 cycle counters (host pointer, may be NULL).  Synchronises the device. */
-int cnerf_debug_profile3(int enable, unsigned long long* out16);
-/* Same for the data-gradient chain kernel (mlp_bwd_tc.cu). */
-int cnerf_debug_profile_chain(int enable, unsigned long long* out16);
-/* Same for the CTA-pair forward kernel (mlp_fwd4.cu). */
-int cnerf_debug_profile4(int enable, unsigned long long* out16);
-/* Debug aid: measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */
-int cnerf_debug_umma_rate(int mode, int n, int iters, int alt, float* out, void* stream);
-/* Debug aid: cycles per N=256 K=16 SS tcgen05.mma, pair != 0: M=256 cta_group::2 on 74 CTA pairs, else M=128 on 148
- * CTAs; traffic bit 0 adds concurrent st.shared traffic, bit 1 a bulk-copy ring fed from src (>= 1 MiB, device).
- * out: 148 device floats. */
-/* Debug aid: TMEM data layout of an M=128 cta_group::2 accumulator (64 rows of a[128,k] per CTA, fp16 hi parts only):
- * dump[2][128][256] = every CTA's TMEM window after d = a b^T. */
-int cnerf_debug_pair_layout(const float* a, const float* b, int n, int k, float* dump, void* stream);
-int cnerf_debug_umma_rate_pair(int pair, int iters, int traffic, const void* src, float* out, void* stream);
 
 #ifdef __cplusplus
 }

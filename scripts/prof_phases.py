@@ -11,7 +11,7 @@ packed = net.packed_weights(); packed.refresh(dict(zip(net.spec.param_names(), [
 n, S = 4096, 192
 pts = torch.randn(n, S, 3, device=dev); vd = torch.nn.functional.normalize(torch.randn(n, 3, device=dev), dim=-1)
 names = {0: "mma total", 1: "mma wait A kblocks", 2: "mma wait enc", 3: "mma wait weights", 4: "mma issue+commit", 8: "epilogue total", 9: "epilogue wait D"}
-IMPL = os.environ.get("CNERF_MLP_IMPL", "4")
+IMPL = os.environ.get("CNERF_MLP_IMPL", "3")
 PROF = "cnerf_debug_profile3" if IMPL == "3" else "cnerf_debug_profile4"
 for mode, dbg in ([("infer", 0), ("infer", 1)] if IMPL == "4" else [("infer", 0), ("train", 0)]):
     fn = (lambda: cn.ops.fused_mlp_forward(packed, pts, vd)) if mode == "infer" else (lambda: cn.ops.fused_mlp_forward_train(packed, pts, vd))

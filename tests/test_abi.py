@@ -7,11 +7,18 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "cnerf.h")
+DEBUG_HEADER = os.path.join(ROOT, "include", "cnerf_debug.h")
 
 
-def declared_functions():
-    src = open(HEADER).read()
+def declared_functions(header=HEADER, experiments=False):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    if "#ifdef CNERF_EXPERIMENTS" in src:
+        head, _, rest = src.partition("#ifdef CNERF_EXPERIMENTS")
+        exp, _, tail = rest.partition("#endif")
+        src = exp if experiments else head + tail
+    elif experiments:
+        src = ""
     return sorted(set(re.findall(r"\b(cnerf_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -34,12 +41,17 @@ def test_library_exports_every_declared_symbol(lib_path):
     for name in declared_functions():
         assert hasattr(dll, name), f"{name} declared in cnerf.h but not exported"
     dll.cnerf_version.restype = ctypes.c_int
-    assert dll.cnerf_version() == 100
+    assert dll.cnerf_version() == 200
+    for name in declared_functions(DEBUG_HEADER):
+        assert hasattr(dll, name), f"{name} declared in cnerf_debug.h but not exported"
 
 
 def test_ctypes_table_mirrors_header(lib_path):
     from consistentnerf_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_functions()
+    assert sorted(_lib.DEBUG_SIGNATURES) == declared_functions(DEBUG_HEADER)
+    assert sorted(_lib.EXPERIMENT_SIGNATURES) == declared_functions(DEBUG_HEADER, experiments=True)
+    assert not any(n.startswith(("cnerf_debug", "cnerf_umma")) for n in _lib.SIGNATURES)      # the boundary carries no debug export
     _lib.load()          # resolves every prototype
 
 

@@ -22,7 +22,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from consistentnerf_b200.distributed import FlatGrads, allreduce_masks, gather_rows, shard_bounds, shard_rays
+    from consistentnerf_b200.distributed import FlatGrads, allreduce_masks, gather_rows, global_mask_counts, shard_bounds, shard_rays
     torch.manual_seed(0)                                   # identical "model" and global batch on every rank
     net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
     rays = torch.randn(101, 6)                             # ragged: 51 + 50
@@ -44,6 +44,32 @@ def _worker(rank, world, port, out_dir):
         assert p.grad.data_ptr() >= flat.flat.data_ptr()   # .grad aliases the flat buffer: no packing copies
         torch.testing.assert_close(p.grad, q.grad, rtol=1e-5, atol=1e-6)
     assert float(flat.extra[0]) == 101.0
+    # zero_grad(set_to_none=True) detaches .grad from the flat buffer: the next reduce re-attaches and keeps the values
+    net.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in net.parameters())
+    flat.zero_()
+    ((net(mine) - tgt[lo:hi]) ** 2).sum().backward()       # autograd makes fresh .grad tensors
+    flat.allreduce()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert flat.flat.data_ptr() <= p.grad.data_ptr() < flat.flat.data_ptr() + flat.flat.numel() * 4
+        torch.testing.assert_close(p.grad / (101 * 3), q.grad, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="async_op"):
+        flat.allreduce(average=True, async_op=True)
+    # two parameter groups (coarse / fine): segment-wise asynchronous reduction == whole-buffer reduction
+    a, b = torch.nn.Linear(4, 4), torch.nn.Linear(4, 2)
+    fg = FlatGrads([list(a.parameters()), list(b.parameters())], extra_slots=2)
+    fg.flat.copy_(torch.arange(fg.flat.numel(), dtype=torch.float32) * (rank + 1))
+    fg.allreduce_group(1)                                  # "fine" first, as autograd orders it
+    fg.allreduce_group(0)
+    fg.wait()
+    torch.testing.assert_close(fg.flat, torch.arange(fg.flat.numel(), dtype=torch.float32) * 3)
+    assert all(getattr(p, "_cnerf_accumulate_in_place", False) for p in fg.params)
+    # global denominators of the masked losses: shard-wise counts sum to the single-process counts
+    gmask = (torch.arange(101) % 3 != 0).float()
+    c = global_mask_counts(gmask[lo:hi], hi - lo)
+    assert c.tolist() == [float((gmask == 1).sum()), float((gmask == 0).sum()), float(gmask.sum()), 101.0]
+    c = global_mask_counts(None, hi - lo, device="cpu")
+    assert c.tolist() == [101.0, 0.0, 101.0, 101.0]
     # hard-mask partials OR-ed across ranks
     part = {7: torch.zeros(10, dtype=torch.uint8), 3: torch.zeros(10, dtype=torch.uint8)}
     part[7][rank] = 1

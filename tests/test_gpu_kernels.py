@@ -135,9 +135,16 @@ def test_umma_a_operand_in_tensor_memory(cn, n, k):
     assert rel_err(d, a.double() @ b.double().t()) < 2e-6
 
 
+def _needs_experiments():
+    from consistentnerf_b200 import _lib
+    if not hasattr(_lib.load(), "cnerf_umma_selftest_pair"):
+        pytest.skip("library built without csrc/experiments (python -m consistentnerf_b200.build --experiments)")
+
+
 @pytest.mark.parametrize("n,k", [(256, 16), (256, 128), (128, 64), (32, 32)])
 def test_umma_cta_pair(cn, n, k):
     """One M=256 tcgen05.mma.cta_group::2 stream for two CTAs: each holds 128 rows of A/D and n/2 rows of B."""
+    _needs_experiments()
     gen = torch.Generator().manual_seed(n * 1000 + k + 2)
     a = torch.randn(256, k, generator=gen)
     b = torch.randn(n, k, generator=gen) * 0.1
@@ -408,7 +415,8 @@ assert worst < 2e-5, worst
 
 @pytest.mark.parametrize("env", [{"CNERF_MLP_IMPL": "4"}])
 def test_opt_in_forward_kernels_match_the_oracle(env):
-    """CNERF_MLP_IMPL=4: CTA-pair ping-pong kernel (mlp_fwd4.cu)."""
+    """CNERF_MLP_IMPL=4: CTA-pair ping-pong kernel (experiments/mlp_fwd4.cu)."""
+    _needs_experiments()
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", _IMPL_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)

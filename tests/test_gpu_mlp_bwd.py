@@ -23,14 +23,14 @@ def g_slot(l):
     return 0 if l == 9 else 65536 + (8 - l) * 131072
 
 
-def decode(rec_u8, tile_bytes, slot, kgroups, lo_off, n_points):
-    """[n_points, 8*kgroups] float64 = hi + lo from the fp16 UMMA tiles of every 128-point record."""
+def decode(rec_u8, tile_bytes, slot, kgroups, lo_off, n_points, use_lo=True):
+    """[n_points, 8*kgroups] float64 = hi (+ lo) from the fp16 UMMA tiles of every 128-point record."""
     rec = rec_u8.cpu().numpy().reshape(-1, tile_bytes)
     out = []
     for t in range(rec.shape[0]):
         hi = rec[t, slot:slot + kgroups * 2048].view(np.float16).reshape(kgroups, 128, 8)
         lo = rec[t, slot + lo_off:slot + lo_off + kgroups * 2048].view(np.float16).reshape(kgroups, 128, 8)
-        v = hi.astype(np.float64) + lo.astype(np.float64)
+        v = hi.astype(np.float64) + (lo.astype(np.float64) if use_lo else 0.0)
         out.append(v.transpose(1, 0, 2).reshape(128, kgroups * 8))
     return torch.from_numpy(np.concatenate(out, 0)[:n_points])
 
@@ -147,6 +147,94 @@ def test_gradient_chain_and_parameter_gradients(setup):
     print("params:", {k: f"{v:.1e}" for k, v in perr.items()})
     assert all(v < 2e-5 for v in errs.values()), errs
     assert all(v < 2e-5 for v in perr.values()), perr
+
+
+# (chain_terms, dw_terms) -> tolerance on the chain's G tiles / on the parameter gradients (max-scale relative).  One-term
+# products round each operand to fp16 (2^-11 per element, unbiased); over the 300 points of this fixture that leaves ~1e-3.
+REDUCED = {"dw16": ((3, 1), 6e-4, 3e-3), "fp16": ((1, 1), 4e-3, 6e-3)}
+
+
+@pytest.mark.parametrize("mode", sorted(REDUCED))
+def test_reduced_precision_backward_modes(setup, mode):
+    """The fp16-operand backward modes (include/cnerf.h K3b): hi-only records, one MMA per MAC."""
+    cn, ref, n = setup["cn"], setup["ref"], setup["n"]
+    terms, tol_g, tol_p = REDUCED[mode]
+    raw, acts = cn.ops.fused_mlp_forward_train(setup["packed"], setup["pts"].to(DEV), setup["vd"].to(DEV), dw_terms=terms[1])
+    assert torch.equal(raw, setup["raw"])                      # the forward result does not depend on the record format
+    grads, rec = cn.ops.fused_mlp_backward(setup["packed"], setup["P"], acts, setup["d_raw"].to(DEV), n, return_record=True,
+                                           terms=terms)
+    torch.cuda.synchronize()
+    amax = float(setup["d_raw"].abs().max())
+    scale = 2.0 ** math.floor(math.log2(256.0 / amax))
+    errs = {"G9": rel_err(decode(rec, GTILE, g_slot(9), 16, 32768, n, use_lo=False) / scale, ref["zv"].grad),
+            "G8": rel_err(decode(rec, GTILE, g_slot(8), 32, 65536, n, use_lo=False) / scale, ref["feat"].grad)}
+    for l in range(7, -1, -1):
+        errs[f"G{l}"] = rel_err(decode(rec, GTILE, g_slot(l), 32, 65536, n, use_lo=False) / scale, ref["pre"][l].grad)
+    perr = {k: rel_err(grads[k], ref["p64"][k].grad) for k in grads}
+    print(mode, "chain:", {k: f"{v:.1e}" for k, v in errs.items()})
+    print(mode, "params:", {k: f"{v:.1e}" for k, v in perr.items()})
+    assert all(v < tol_g for v in errs.values()), errs
+    assert all(v < tol_p for v in perr.values()), perr
+    # direction of the full gradient: what a training step consumes
+    a = torch.cat([grads[k].double().cpu().reshape(-1) for k in sorted(grads)])
+    b = torch.cat([ref["p64"][k].grad.reshape(-1) for k in sorted(grads)])
+    cos = float((a * b).sum() / (a.norm() * b.norm()))
+    assert cos > 1.0 - 1e-5, cos
+
+
+def test_grad_precision_switch_reaches_the_autograd_path(setup):
+    cn, net = setup["cn"], setup["net"]
+    e, _ = cn.get_embedder(10)
+    ev, _ = cn.get_embedder(4)
+    pts, vd = setup["pts"].to(DEV), setup["vd"].to(DEV)
+    g = torch.randn(5, 60, 4, generator=torch.Generator().manual_seed(9)).to(DEV) * 1e-5
+    out = {}
+    prev = cn.ops.grad_precision()
+    try:
+        for mode in ("split", "dw16", "fp16"):
+            cn.ops.set_grad_precision(mode)
+            net.zero_grad()
+            cn.run_network(pts, vd, net, e, ev).backward(g)
+            out[mode] = {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None}
+    finally:
+        cn.ops.set_grad_precision(prev)
+    for mode in ("dw16", "fp16"):
+        worst = max(rel_err(out[mode][k], out["split"][k]) for k in out["split"])
+        assert 0.0 < worst < 6e-3, (mode, worst)                 # really a different arithmetic, and close
+    with pytest.raises(ValueError):
+        cn.ops.set_grad_precision("bf16")
+
+
+def test_inplace_accumulation_is_opt_in(setup):
+    """parameters that merely own a .grad get their gradients through autograd (torch.autograd.grad works,
+    AccumulateGrad hooks fire); only FlatGrads-marked parameters take the in-place path."""
+    cn, net = setup["cn"], setup["net"]
+    e, _ = cn.get_embedder(10)
+    ev, _ = cn.get_embedder(4)
+    pts, vd = setup["pts"].to(DEV), setup["vd"].to(DEV)
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)                             # every parameter owns a .grad, none is marked
+    params = net.hot_params()
+    out = cn.run_network(pts, vd, net, e, ev)
+    got = torch.autograd.grad(out.sum() * 1e-6, params)
+    assert all(g is not None and float(g.abs().max()) > 0 for g in got)
+    assert all(float(p.grad.abs().max()) == 0.0 for p in params)          # .grad untouched by autograd.grad
+    fired = []
+    h = params[0].register_post_accumulate_grad_hook(lambda p: fired.append(1))
+    (cn.run_network(pts, vd, net, e, ev).sum() * 1e-6).backward()
+    h.remove()
+    assert fired == [1]
+    from consistentnerf_b200.distributed import FlatGrads
+    ref = [p.grad.clone() for p in params]
+    flat = FlatGrads(params)
+    flat.zero_()
+    (cn.run_network(pts, vd, net, e, ev).sum() * 1e-6).backward()
+    for p, r in zip(params, ref):
+        assert p.grad.data_ptr() >= flat.flat.data_ptr() and rel_err(p.grad, r) < 1e-6
+    for p in net.parameters():
+        p.grad = None
+        if hasattr(p, "_cnerf_accumulate_in_place"):
+            del p._cnerf_accumulate_in_place
 
 
 def test_autograd_path_matches_cuda_core_backward(setup):
