@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import importlib
 import sys
-import types
 
 import torch
 
@@ -58,55 +57,39 @@ def patch(module, with_depth=None):
 
 
 def install_io_stubs():
-    """Empty stand-ins for modules the reference imports only for I/O / logging when they are absent."""
-    for name in ["imageio", "ipdb", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "configargparse",
-                 "tensorboardX", "pytorch_msssim", "lpips"]:
-        try:
-            importlib.import_module(name)
-        except Exception:
-            sys.modules[name] = types.ModuleType(name)
-    mpl = sys.modules["matplotlib"]
-    if not hasattr(mpl, "__path__"):
-        mpl.__path__ = []
-        mpl.pyplot = sys.modules["matplotlib.pyplot"]
-        mpl.cm = sys.modules["matplotlib.cm"]
-    lp = sys.modules["lpips"]
-    if not hasattr(lp, "LPIPS"):
-        class _NoLPIPS:
-            def __init__(self, *a, **k):
-                pass
+    """Make the I/O-only modules the reference imports resolvable when they are absent (imageio, configargparse, matplotlib,
+    tensorboardX, ipdb, pytorch_msssim, lpips): functional stand-ins from ``consistentnerf_b200/shims`` are appended to
+    ``sys.path``, so an installed original always wins."""
+    from . import shims
+    return shims.install()
 
-            def to(self, *a, **k):
-                return self
 
-            def __call__(self, *a, **k):
-                raise RuntimeError("lpips is not installed in this image")
-        lp.LPIPS = _NoLPIPS
-    tb = sys.modules["tensorboardX"]
-    if not hasattr(tb, "SummaryWriter"):
-        class _NullWriter:
-            def __init__(self, *a, **k):
-                pass
-
-            def __getattr__(self, _):
-                return lambda *a, **k: None
-        tb.SummaryWriter = _NullWriter
-    ms = sys.modules["pytorch_msssim"]
-    for n in ("ssim", "ms_ssim"):
-        if not hasattr(ms, n):
-            setattr(ms, n, lambda *a, **k: (_ for _ in ()).throw(RuntimeError("pytorch_msssim is not installed")))
+def bound_iterations(module, max_iters: int):
+    """Stop the script's training loop after ``max_iters`` steps: run_nerf.py hard-codes 200 001 iterations (NP/run_nerf.py:704)
+    and iterates with the module-global ``trange``."""
+    def bounded(a, b=None, *args, **kwargs):
+        lo, hi = (0, a) if b is None else (a, b)
+        return range(lo, min(hi, lo + int(max_iters)))
+    module.trange = bounded
 
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
-        print("usage: python -m consistentnerf_b200.dropin <reference_script_module> [script args...]")
+        print("usage: python -m consistentnerf_b200.dropin <reference_script_module> [--cnerf_max_iters N] [script args...]")
         return 2
     script, rest = argv[0], argv[1:]
+    max_iters = None
+    if "--cnerf_max_iters" in rest:                   # launcher option, not passed on to the script
+        i = rest.index("--cnerf_max_iters")
+        max_iters = int(rest[i + 1])
+        del rest[i:i + 2]
     install_io_stubs()
     module = importlib.import_module(script)
     patched = patch(module)
     print(f"[consistentnerf_b200] patched {script}: {', '.join(patched)}")
+    if max_iters is not None:
+        bound_iterations(module, max_iters)
     torch.set_default_tensor_type("torch.cuda.FloatTensor")
     sys.argv = [script + ".py"] + rest
     return module.train()

@@ -134,7 +134,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     rgbs = np.empty((n, H, W, 3), dtype=np.float32)
     disps = np.empty((n, H, W), dtype=np.float32)
     accs = np.empty((n, H, W), dtype=np.float32)
-    pinned = [torch.empty((H, W, 5), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pinned = [torch.empty((H, W, 5), dtype=torch.float32, device="cpu", pin_memory=True) for _ in range(2)]
     staged = [torch.empty((H, W, 5), dtype=torch.float32, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     done = [None, None]
