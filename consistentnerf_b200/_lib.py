@@ -36,9 +36,9 @@ SIGNATURES = {
     "cnerf_weights_create": (_I, [POINTER(c_void_p)]),
     "cnerf_weights_destroy": (None, [_P]),
     "cnerf_weights_refresh": (_I, [_P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "cnerf_mlp_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "cnerf_mlp_fwd": (_I, [_P, _P, _P, _I, _I, _P, _I, _P]),
     "cnerf_mlp_acts_bytes": (c_int64, [c_int64]),
-    "cnerf_mlp_fwd_train": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "cnerf_mlp_fwd_train": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P]),
     "cnerf_mlp_grads_bytes": (c_int64, [c_int64]),
     "cnerf_mlp_bwd_workspace_bytes": (c_int64, []),
     "cnerf_mlp_bwd": (_I, [_P, _P, _P, _P, _I, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),

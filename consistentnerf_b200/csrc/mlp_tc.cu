@@ -254,6 +254,8 @@ int launch_fused4(const uint8_t* stream4, const float* misc, const float* pts, c
 #endif
 int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, uint8_t* acts, int record_lo, int terms, cudaStream_t st);
+int launch_fused5(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,         // mlp_fwd5.cu
+                  int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
 }
 
 // The product runs the single-CTA N=256 kernel (mlp_fwd3.cu).  A build with CNERF_EXPERIMENTS (python -m
@@ -317,8 +319,11 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
     return CNERF_OK;
 }
 
+// fwd_terms 3: three-term fp16 hi/lo forward (mlp_fwd3.cu); 1: fp16-operand forward, two tiles in flight (mlp_fwd5.cu)
 static int launch_mlp(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                      float* raw, void* acts, int record_lo, int terms, void* stream, const char* who) {
+                      float* raw, void* acts, int record_lo, int terms, int fwd_terms, void* stream, const char* who) {
+    CNERF_REQUIRE(fwd_terms == 1 || fwd_terms == 3, "%s: fwd_terms must be 1 (fp16 operands) or 3 (hi/lo split)", who);
+    CNERF_REQUIRE(!(fwd_terms == 1 && acts && record_lo), "%s: the fp16 forward writes an fp16 record (dw_terms must be 1)", who);
     CNERF_REQUIRE(w && w->packed, "%s: weights handle not packed (call cnerf_weights_refresh)", who);
     CNERF_REQUIRE(pts && viewdirs && raw, "%s: null pointer", who);
     CNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "%s: bad sizes", who);
@@ -330,13 +335,15 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     if (fwd_impl() == 4 && !acts && terms == 7)      // the CTA-pair experiment is inference only; training runs the single-CTA kernel
         return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, as_stream(stream));
 #endif
+    if (fwd_terms == 1 && terms == 7)
+        return launch_fused5(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, record_lo, terms,
                          as_stream(stream));
 }
 
 extern "C" int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                             float* raw, void* stream) {
-    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, 7, stream, "cnerf_mlp_fwd");
+                             float* raw, int fwd_terms, void* stream) {
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, 7, fwd_terms, stream, "cnerf_mlp_fwd");
 }
 
 // Measurement only (include/cnerf_debug.h): the forward with a subset of the three partial products of the fp16 hi/lo split
@@ -344,7 +351,7 @@ extern "C" int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const flo
 extern "C" int cnerf_debug_mlp_fwd_terms(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
                                          int n_samples, float* raw, int terms, void* stream) {
     CNERF_REQUIRE((terms & 1) && terms > 0 && terms < 8, "cnerf_debug_mlp_fwd_terms: terms must contain bit 0 and be < 8");
-    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, terms == 7 ? 15 : terms, stream, "cnerf_debug_mlp_fwd_terms");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, nullptr, 0, terms == 7 ? 15 : terms, 3, stream, "cnerf_debug_mlp_fwd_terms");
 }
 
 extern "C" int64_t cnerf_mlp_acts_bytes(int64_t n_points) {
@@ -352,10 +359,10 @@ extern "C" int64_t cnerf_mlp_acts_bytes(int64_t n_points) {
 }
 
 extern "C" int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
-                                   int n_samples, float* raw, void* acts, int dw_terms, void* stream) {
+                                   int n_samples, float* raw, void* acts, int fwd_terms, int dw_terms, void* stream) {
     CNERF_REQUIRE(acts, "cnerf_mlp_fwd_train: null activation record buffer");
     CNERF_REQUIRE(dw_terms == 1 || dw_terms == 3, "cnerf_mlp_fwd_train: dw_terms must be 1 (fp16 record) or 3 (hi/lo record)");
-    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, acts, dw_terms == 3, 7, stream, "cnerf_mlp_fwd_train");
+    return launch_mlp(w, pts, viewdirs, n_rays, n_samples, raw, acts, dw_terms == 3, 7, fwd_terms, stream, "cnerf_mlp_fwd_train");
 }
 
 extern "C" int cnerf_umma_selftest(const float* a, const float* b, int n, int k, float* d, void* stream) {

@@ -385,11 +385,34 @@ class PackedWeights:
         self._key = key
 
 
-def fused_mlp_forward(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor) -> torch.Tensor:
+# Precision of the fused forward (include/cnerf.h, fwd_terms): "split" = fp16 hi/lo three-term products (fp32-equivalent),
+# "fp16" = fp16 operands with fp32 accumulation, one MMA per MAC, two tiles in flight per SM (csrc/mlp_fwd5.cu).
+FWD_PRECISIONS = {"split": 3, "fp16": 1}
+DEFAULT_FWD_PRECISION = "split"
+_fwd_precision = os.environ.get("CNERF_FWD_PRECISION", DEFAULT_FWD_PRECISION)
+if _fwd_precision not in FWD_PRECISIONS:
+    raise ValueError(f"CNERF_FWD_PRECISION={_fwd_precision!r}: expected one of {sorted(FWD_PRECISIONS)}")
+
+
+def set_forward_precision(name: str) -> str:
+    """Select the forward precision for subsequent calls (returns the previous setting)."""
+    global _fwd_precision
+    if name not in FWD_PRECISIONS:
+        raise ValueError(f"forward precision {name!r}: expected one of {sorted(FWD_PRECISIONS)}")
+    prev, _fwd_precision = _fwd_precision, name
+    return prev
+
+
+def forward_precision() -> str:
+    return _fwd_precision
+
+
+def fused_mlp_forward(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor, fwd_terms: Optional[int] = None) -> torch.Tensor:
     """pts [n,S,3], viewdirs [n,3] -> raw [n,S,4] (K2+K3 on tensor cores)."""
     n, S = pts.shape[0], pts.shape[1]
     raw = torch.empty((n, S, 4), device=pts.device, dtype=_F32)
-    call("cnerf_mlp_fwd", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), stream())
+    ft = FWD_PRECISIONS[_fwd_precision] if fwd_terms is None else int(fwd_terms)
+    call("cnerf_mlp_fwd", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ft, stream())
     return raw
 
 
@@ -422,13 +445,18 @@ def grad_precision() -> str:
     return _grad_precision
 
 
-def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor, dw_terms: int = 3):
-    """Training-mode forward: raw [n,S,4] plus the activation record the tensor-core backward reads."""
+def fused_mlp_forward_train(packed: PackedWeights, pts: torch.Tensor, viewdirs: torch.Tensor, dw_terms: int = 3,
+                            fwd_terms: Optional[int] = None):
+    """Training-mode forward: raw [n,S,4] plus the activation record the tensor-core backward reads.  The fp16 forward
+    writes an fp16 record: with a three-term weight gradient (dw_terms == 3) the three-term forward runs instead."""
+    ft = FWD_PRECISIONS[_fwd_precision] if fwd_terms is None else int(fwd_terms)
+    if int(dw_terms) == 3:
+        ft = 3
     n, S = pts.shape[0], pts.shape[1]
     raw = torch.empty((n, S, 4), device=pts.device, dtype=_F32)
     nbytes = int(_lib.load().cnerf_mlp_acts_bytes(n * S))
     acts = torch.empty(nbytes, device=pts.device, dtype=torch.uint8)
-    call("cnerf_mlp_fwd_train", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ptr(acts), int(dw_terms), stream())
+    call("cnerf_mlp_fwd_train", packed.handle, ptr(_f32c(pts)), ptr(_f32c(viewdirs)), n, S, ptr(raw), ptr(acts), ft, int(dw_terms), stream())
     return raw, acts
 
 

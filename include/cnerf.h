@@ -108,10 +108,15 @@ int cnerf_linear_bwd_weight(const float* dy, int lddy, const float* y, int ldy, 
  * (run_network NP/run_nerf.py:37-52 + NeRF.forward).  Canonical architecture only:
  * D=8, W=256, skips=[4], use_viewdirs, multires=10, multires_views=4.
  *
- * Precision of the forward (inference and training): every fp32 operand is split into two
- * fp16 terms (hi + lo); each product is evaluated as hi*hi + hi*lo + lo*hi on the tensor cores
- * with fp32 accumulation in TMEM, i.e. ~2^-21 relative per product -- fp32-equivalent, 3 MMAs
- * per algorithmic MAC.
+ * Precision of the forward (inference and training), chosen by the caller with fwd_terms:
+ *   fwd_terms    3: every fp32 operand is split into two fp16 terms (hi + lo); each product is
+ *                   evaluated as hi*hi + hi*lo + lo*hi on the tensor cores with fp32 accumulation
+ *                   in TMEM, i.e. ~2^-21 relative per product -- fp32-equivalent, 3 MMAs per
+ *                   algorithmic MAC (measured: rendered maps within 7e-7 of the fp64 oracle);
+ *                1: fp16 operands, ONE MMA per MAC, fp32 accumulation; the A operand is half as
+ *                   large, so two 128-point tiles are in flight per SM (measured on workload A:
+ *                   rendered maps within 2e-5 of the fp64 oracle -- bar 1e-4 -- raw within 1.1e-4).
+ *                   In training it writes an fp16 record, i.e. it requires dw_terms == 1.
  *
  * Precision of the backward (K3b) is chosen by the caller with two arguments:
  *   chain_terms  3: the data-gradient chain G_{l-1} = (G_l W_l)[h>0] runs the same three-term split;
@@ -136,14 +141,14 @@ int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w, const flo
                           const float* rgb_w, const float* rgb_b, void* stream);
 /* raw[n_rays*n_samples, 4] = NeRF(embed(pts), embed(viewdirs[ray])). */
 int cnerf_mlp_fwd(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays,
-                  int n_samples, float* raw, void* stream);
+                  int n_samples, float* raw, int fwd_terms, void* stream);
 /* Training-mode forward: same result as cnerf_mlp_fwd, and every layer's A operand (encodings, post-activation
  * outputs; fp16 hi tiles, plus the lo tiles when dw_terms == 3) plus the ReLU sign bits are streamed into `acts`
  * (cnerf_mlp_acts_bytes(n_rays*n_samples) bytes, device: 1 345 536 per 128 points, opaque to the caller) for
  * cnerf_mlp_bwd.  With dw_terms == 1 the lo slots of the record are left untouched (never read). */
 int64_t cnerf_mlp_acts_bytes(int64_t n_points);
 int cnerf_mlp_fwd_train(const cnerf_weights* w, const float* pts, const float* viewdirs, int n_rays, int n_samples,
-                        float* raw, void* acts, int dw_terms, void* stream);
+                        float* raw, void* acts, int fwd_terms, int dw_terms, void* stream);
 /* K3b backward on tensor cores (autograd of run_network w.r.t. the parameters; loss.backward() of
  * NP/run_nerf_view.py:1982 for this module).  d_raw [n_points,4]; `acts` from cnerf_mlp_fwd_train with the SAME packed
  * weights; `grads_rec` scratch of cnerf_mlp_grads_bytes(n_points) bytes; `workspace` of

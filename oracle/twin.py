@@ -372,13 +372,14 @@ def reference_workload_a(device: str, n_rays: int, steps: int, warmup: int, mode
     shims.install()
     sys.path.insert(0, REF)
     import run_nerf as m
+    import bench
+    batches = [bench.make_batch(n_rays, b) for b in range(8)]       # drawn on the host BEFORE the default tensor type changes
     if device == "cuda":
         torch.set_default_tensor_type("torch.cuda.FloatTensor")
         m.device = torch.device("cuda")
     else:
         m.device = torch.device("cpu")
         torch.set_num_threads(threads or os.cpu_count() or 1)
-    import bench
     p = m.config_parser()
     args = p.parse_args(["--expname", "eager", "--basedir", "/tmp/cnerf_eager_logs", "--use_viewdirs", "--white_bkgd", "--N_samples", "64",
                          "--N_importance", "128", "--no_reload", "--dataset_type", "blender", "--chunk", "32768", "--netchunk", "65536"])
@@ -391,7 +392,7 @@ def reference_workload_a(device: str, n_rays: int, steps: int, warmup: int, mode
     kw = kw_train if train else kw_test
 
     def step(i):
-        o, d, tgt, prior, mask = bench.make_batch(n_rays, i % 8)
+        o, d, tgt, prior, mask = batches[i % 8]
         rays = torch.stack([o, d], 0).to(m.device)
         tgt = tgt.to(m.device)
         if train:
