@@ -62,6 +62,7 @@ DEBUG_SIGNATURES = {
     "cnerf_umma_selftest_ts": (_I, [_P, _P, _I, _I, _P, _P]),
     "cnerf_debug_mlp_fwd_terms": (_I, [_P, _P, _P, _I, _I, _P, _I, _P]),
     "cnerf_debug_profile3": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
+    "cnerf_debug_profile5": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_debug_profile_chain": (_I, [_I, POINTER(ctypes.c_ulonglong)]),
     "cnerf_debug_umma_rate": (_I, [_I, _I, _I, _I, _P, _P]),
 }

@@ -40,7 +40,12 @@ __device__ __forceinline__ void emit_hi(uint32_t base, uint32_t row, uint32_t kg
     st_shared_v4(base + kg * kLBO + row * 16, h[0], h[1], h[2], h[3]);
 }
 
-template <int kSave>
+__device__ unsigned long long g_prof5[16];
+#define PROF5_T0() long long pt0__ = kProf ? clock64() : 0
+#define PROF5_ADD(var) do { if (kProf) { long long t__ = clock64(); var += t__ - pt0__; } } while (0)
+
+// kProf: instrumented instantiation for the phase profile (cnerf_debug_profile5); the production kernels carry none of it
+template <int kSave, bool kProf>
 __global__ void __launch_bounds__(k5Threads, 1)
 mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, int n_points, int n_samples, int n_rays, float* __restrict__ raw,
@@ -93,6 +98,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         const uint64_t b256 = smem_desc_any(sbase + k5Ring, 4096, 128), b128 = smem_desc(sbase + k5Ring);
         const uint64_t stream_pol = l2_policy_evict_first();
         uint32_t u = 0;
+        long long pw_a = 0, pw_full = 0, pw_issue = 0, pw_rec = 0, p_start = kProf ? clock64() : 0;
         for (int it = 0; it < n_iter; ++it) {
 #pragma unroll 1
             for (int layer = 0; layer < 10; ++layer) {
@@ -105,7 +111,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     const uint32_t act = sbase + k5Act + (uint32_t)s * 65536, emb = sbase + k5Emb + (uint32_t)s * 16384;
                     const uint64_t act_d = smem_desc(act), emb_d = smem_desc(emb);
                     const uint32_t d = tmem + (uint32_t)s * 256;
-                    mbar_wait(bar_aready + 8 * s, (uint32_t)(it * 10 + layer) & 1);
+                    { PROF5_T0(); mbar_wait(bar_aready + 8 * s, (uint32_t)(it * 10 + layer) & 1); PROF5_ADD(pw_a); }
                     tc_fence_after();
                     if (kSave && elect_one()) {      // the operand this layer reads is final: stream it to the record (hi halves)
                         if (layer == 0) bulk_s2g_hint(rec + kSlotE, emb, 16384, stream_pol);
@@ -120,8 +126,9 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 #pragma unroll 1
                     for (int j = 0; j < nb; ++j, ++u) {
                         const uint32_t st = u % k5Stages, ph = (u / k5Stages) & 1;
-                        mbar_wait(bar_full + 8 * st, ph);
+                        { PROF5_T0(); mbar_wait(bar_full + 8 * st, ph); PROF5_ADD(pw_full); }
                         tc_fence_after();
+                        PROF5_T0();
                         if (elect_one()) {
                             const uint32_t acc = j == 0 ? 0u : 1u;
                             if (layer < 9) {
@@ -140,6 +147,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                             umma_commit(bar_empty + 8 * st);
                         }
                         __syncwarp();
+                        PROF5_ADD(pw_issue);
                     }
                     // training: the previous tile's views output (staged in this slot's A tile by its last epilogue) goes to the record
                     // now, behind layer 0's MMAs (which read the encoding tile only); it must have left before epilogue 0 rewrites A
@@ -148,13 +156,22 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         if (elect_one()) { bulk_s2g_hint(rec - (size_t)2 * gridDim.x * kTileBytes + kSlotHV, act, 32768, stream_pol); bulk_commit(); }
                         __syncwarp();
                     }
-                    if (elect_one()) {
-                        if (kSave) bulk_wait_read0();       // the epilogue overwrites the operand tile once it sees this layer done
-                        umma_commit(bar_dfull + 8 * s);
+                    {
+                        PROF5_T0();
+                        if (elect_one()) {
+                            if (kSave) bulk_wait_read0();       // the epilogue overwrites the operand tile once it sees this layer done
+                            umma_commit(bar_dfull + 8 * s);
+                        }
+                        __syncwarp();
+                        PROF5_ADD(pw_rec);
                     }
-                    __syncwarp();
                 }
             }
+        }
+        if (kProf && lane == 0) {
+            atomicAdd(&g_prof5[0], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_prof5[1], (unsigned long long)pw_a); atomicAdd(&g_prof5[3], (unsigned long long)pw_full);
+            atomicAdd(&g_prof5[4], (unsigned long long)pw_issue); atomicAdd(&g_prof5[5], (unsigned long long)pw_rec);
         }
         if (kSave) {      // views outputs of the last tile of each slot
             for (int s = 0; s < 2; ++s) {
@@ -195,6 +212,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         };
         for (int s = 0; s < 2; ++s)
             if (s < my_tiles) publish_encoding((int)blockIdx.x + s * (int)gridDim.x, s);
+        long long pw_d = 0, pw_ld = 0, pw_body = 0, p_start = kProf ? clock64() : 0;
         float alpha0 = 0.f, alpha1 = 0.f;                 // alpha_linear partial dot products of the two slots (scalars: no dynamic indexing)
         for (int it = 0; it < n_iter; ++it) {
 #pragma unroll 1
@@ -207,8 +225,9 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                     const int grow = tile * (int)kRows + (int)row;
                     const bool valid = grow < n_points;
                     const uint32_t ab = sbase + k5Act + (uint32_t)s * 65536, eb = sbase + k5Emb + (uint32_t)s * 16384;
-                    mbar_wait(bar_dfull + 8 * s, (uint32_t)(it * 10 + layer) & 1);
+                    { PROF5_T0(); mbar_wait(bar_dfull + 8 * s, (uint32_t)(it * 10 + layer) & 1); PROF5_ADD(pw_d); }
                     tc_fence_after();
+                    PROF5_T0();
                     if (layer < 9) {
                         if (layer == 0) { if (s) alpha1 = 0.f; else alpha0 = 0.f; }
                         if (layer == 5) {
@@ -231,9 +250,11 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 #pragma unroll
                         for (uint32_t half = 0; half < 2; ++half) {
                             float v[32];
+                            long long tl0 = kProf ? clock64() : 0;
 #pragma unroll
                             for (uint32_t k4 = 0; k4 < 4; ++k4) tmem_ld8(dcol + (half * 4 + k4) * 32, v + 8 * k4);
                             tmem_ld_wait();
+                            if (kProf) pw_ld += clock64() - tl0;
 #pragma unroll
                             for (uint32_t k4 = 0; k4 < 4; ++k4) {
                                 const uint32_t kb = half * 4 + k4;
@@ -314,8 +335,14 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         }
                         named_bar_sync(1, 512);      // the scratch lives in the A tile the slot's next epilogue rewrites
                     }
+                    PROF5_ADD(pw_body);
                 }
             }
+        }
+        if (kProf && lane == 0 && warp == 0) {
+            atomicAdd(&g_prof5[8], (unsigned long long)(clock64() - p_start));
+            atomicAdd(&g_prof5[9], (unsigned long long)pw_d); atomicAdd(&g_prof5[10], (unsigned long long)pw_ld);
+            atomicAdd(&g_prof5[11], (unsigned long long)pw_body);
         }
     }
     tc_fence_before();
@@ -323,21 +350,41 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
+static int g_prof5_host = 0;
+
 int launch_fused5(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5Smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_fused5_kernel)");
         attr_set = true;
     }
     const int tiles = ceil_div(n_points, (int)kRows);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    if (acts) mlp_fused5_kernel<1><<<grid, k5Threads, k5Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts);
-    else mlp_fused5_kernel<0><<<grid, k5Threads, k5Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, nullptr);
+#define CNERF_F5(S, P) mlp_fused5_kernel<S, P><<<grid, k5Threads, k5Smem, st>>>(stream3, misc, pts, viewdirs, n_points, n_samples, n_rays, raw, acts)
+    if (g_prof5_host) { if (acts) CNERF_F5(1, true); else CNERF_F5(0, true); }
+    else { if (acts) CNERF_F5(1, false); else CNERF_F5(0, false); }
+#undef CNERF_F5
     CNERF_LAUNCH_CHECK("mlp_fused5_kernel");
     return CNERF_OK;
 }
 
 }  // namespace cnerf
+
+// Debug: in-kernel phase profile of mlp_fused5_kernel (cycles summed over CTAs):
+//  [0] MMA warp total  [1] wait A operand  [3] wait weights  [4] MMA issue + commit  [5] record read-wait + layer commit
+//  [8] epilogue warp 0 total  [9] wait D  [10] tcgen05.ld + wait  [11] epilogue body (incl. [10])
+extern "C" int cnerf_debug_profile5(int enable, unsigned long long* out16) {
+    using namespace cnerf;
+    unsigned long long zero[16] = {0};
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out16) e = cudaMemcpyFromSymbol(out16, g_prof5, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_prof5, zero, sizeof(zero));
+    if (e != cudaSuccess) return check_cuda(e, "cnerf_debug_profile5");
+    g_prof5_host = enable & 1;
+    return CNERF_OK;
+}

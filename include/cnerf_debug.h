@@ -40,6 +40,8 @@ int cnerf_debug_mlp_fwd_terms(const cnerf_weights* w, const float* pts, const fl
 /* Enable/disable the in-kernel phase profile of the fused forward kernel (mlp_fwd3.cu) and read + clear its 16 cycle
  * counters (host pointer, may be NULL).  Synchronises the device. */
 int cnerf_debug_profile3(int enable, unsigned long long* out16);
+/* Same for the fp16 two-tile forward kernel (mlp_fwd5.cu). */
+int cnerf_debug_profile5(int enable, unsigned long long* out16);
 /* Same for the data-gradient chain kernel (mlp_bwd_tc.cu). */
 int cnerf_debug_profile_chain(int enable, unsigned long long* out16);
 /* Measured cycles per tcgen05.mma (M=128, N=n, K=16; mode 0 = SS, 1 = TS) on every SM; out: 148 device floats. */

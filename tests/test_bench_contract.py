@@ -23,7 +23,13 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "rays/sec" and d["unit"] == "rays/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["gpu_launches"] == 0 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "sample" in cb
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "sample" in cb
+    sys.path.insert(0, ROOT)
+    from oracle import build_ref
+    if build_ref.available():      # the unmodified reference (oracle/_ref) at the full 4096-ray batch: same config as the B200 arm
+        assert cb["kind"] == "reference" and cb["same_config"] is True and "4096 rays/step" in cb["sample"] and "UNMODIFIED" in cb["sample"]
+    else:
+        assert cb["kind"] == "port" and cb["same_config"] is False
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

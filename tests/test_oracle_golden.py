@@ -134,3 +134,50 @@ def test_sum_order_restatement_matches_torch_cpu():
     w = (g["weights"] + np.float32(1e-5)).astype(np.float32)
     tot = np.array([O.aten_cpu_sum_f32(r) for r in w], dtype=np.float32)
     assert np.array_equal(tot, torch.from_numpy(w).sum(-1).numpy())
+
+
+# ---- round-2 goldens (oracle/make_golden_r2.py): NDC render, coarse-only / no view directions, hard mask at chunk 5120 ----
+NOVIEW = dict(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=4, skips=(4,), use_viewdirs=False)
+
+
+def test_render_ndc_golden():
+    g = load_golden("render_ndc")
+    H, W = (int(v) for v in g["hw"])
+    ro, rd = O.pixel_rays(H, W, g["K"], t(g["c2w"]))
+    close(ro.reshape(-1, 3), g["rays_o"], rtol=0, atol=0)
+    rays = O.pack_rays(ro.reshape(-1, 3), rd.reshape(-1, 3), 0.0, 1.0, True, ndc=(H, W, float(g["focal"])))
+    pc = O.make_params(int(g["seeds"][0]), sigma_bias=float(g["sigma_bias"]), **ARCH)
+    pf = O.make_params(int(g["seeds"][1]), sigma_bias=float(g["sigma_bias"]), **ARCH)
+    out = O.render_rays(rays, pc, pf, ARCH, n_samples=64, n_importance=128, white_bkgd=False, retraw=True)
+    for k in ("rgb_map", "acc_map", "depth_map", "rgb0", "acc0", "depth0", "z_std"):
+        close(out[k], g[k].reshape(H * W, *g[k].shape[2:]), rtol=3e-5, atol=3e-6)
+    close(out["raw"], g["raw"].reshape(H * W, 192, 4), rtol=3e-5, atol=3e-6)
+
+
+def test_render_noview_coarse_only_golden():
+    g = load_golden("render_noview")
+    rays = O.pack_rays(t(g["rays_o"]), t(g["rays_d"]), float(g["near"]), float(g["far"]), False)
+    assert rays.shape[1] == 8
+    p = O.make_params(int(g["seed"]), sigma_bias=float(g["sigma_bias"]), **NOVIEW)
+    out = O.render_rays(rays, p, None, NOVIEW, n_samples=32, n_importance=0, white_bkgd=True, retraw=True)
+    for k in ("rgb_map", "acc_map", "raw"):
+        close(out[k], g[k], rtol=3e-5, atol=3e-6)
+    close(out["disp_map"], g["disp_map"], rtol=1e-4, atol=1e-6)
+    assert "rgb0" not in out
+
+
+def test_hard_mask_at_the_real_chunk_size_golden():
+    g = load_golden("hardmask_big")
+    n = g["mask"].shape[0]
+    assert n == 16128 and int(g["chunk"]) == 5120 and n // 5120 == 3          # three full chunks + a ragged one
+    total = torch.zeros(n, dtype=torch.bool)
+    for r in range(2):
+        m = O.hard_mask_pair(t(g["rays_o"]), t(g["rays_d"]), t(g["depth_tgt"]).reshape(-1), t(g["w2c_refs"][r]), t(g["K"]),
+                             t(g["depth_refs"][r]), thr0=float(g["thr0"]), chunk=5120)
+        assert np.array_equal(m.numpy(), g[f"mask_ref{r}"]), r
+        total |= m
+    assert np.array_equal(total.numpy(), g["mask"]) and 0 < int(total.sum()) < n
+    # the chunk size is a semantic parameter: a different chunking gives a different mask on this scene
+    other = O.hard_mask_pair(t(g["rays_o"]), t(g["rays_d"]), t(g["depth_tgt"]).reshape(-1), t(g["w2c_refs"][0]), t(g["K"]),
+                             t(g["depth_refs"][0]), thr0=float(g["thr0"]), chunk=16128)
+    assert not np.array_equal(other.numpy(), g["mask_ref0"])
