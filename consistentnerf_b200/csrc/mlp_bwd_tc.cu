@@ -80,7 +80,7 @@ pack_bwd_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
     const int L = 9 - step;
     const float* W = p.w[L];
     const int ld = p.ld[L], col0 = (L == 5) ? 63 : 0;
-    uint8_t* dst = stream + (size_t)b * kBlockBytes;
+    uint8_t* dst = stream + ((size_t)blockIdx.y * kC3NumBlocks + b) * kBlockBytes;      // blockIdx.y: replica
     for (int u = threadIdx.x; u < 512; u += 256) {
         const int r = u & 255, kg = u >> 8;
         float v[8];
@@ -142,6 +142,7 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
     const uint32_t bar_sdone = bar_aready + 64;                  //      the tile's last G stores have left shared memory
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kC3TmemSlot);
     const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+    wstream += (size_t)(blockIdx.x % kWeightReplicas) * kC3NumBlocks * kBlockBytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kC3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -369,18 +370,22 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwMaxStages, bar_acc = bar_empty + 8 * kDwMaxStages;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kDwBars + 112);
+    // three-term mode: a stage holds 32 points of every source as [hi | lo] k-group rows of 512 B; fp16 mode: 64 points of the
+    // hi halves as rows of 1024 B (the same stage size: half the barrier hand-shakes per byte)
     const uint32_t nhalf = P.terms == 1 ? 1u : 2u;                          // operand halves per source in a stage
-    const uint32_t n_stages = P.terms == 1 ? kDwMaxStages : kDwStages, stage_stride = P.terms == 1 ? kDwStageBytes / 2 : kDwStageBytes;
+    const uint32_t qb = P.terms == 1 ? 2 * kQuarter : kQuarter;             // bytes of one k-group row in a stage
+    const uint32_t ksteps = qb / 256, per_tile = 128 * 16 / qb;             // K = 16 MMA steps per stage, stages per 128-point tile
+    const uint32_t n_stages = kDwStages, stage_stride = kDwStageBytes;
 
     // contiguous tile range of this CTA
     const int per = num_tiles / gridDim.x, rem = num_tiles % gridDim.x;
     const int t0 = blockIdx.x * per + min((int)blockIdx.x, rem), t1 = t0 + per + ((int)blockIdx.x < rem ? 1 : 0);
-    const int n_stage_iters = (t1 - t0) * 4;
+    const int n_stage_iters = (t1 - t0) * (P.terms == 1 ? 2 : 4);
 
     // stage map: A sources then X sources, each [hi kgroups*512 | lo kgroups*512]
     uint32_t a_off[2], x_off[2], off = 0;
-    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += nhalf * P.a[i].kgroups * kQuarter; }
-    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += nhalf * P.x[j].kgroups * kQuarter; }
+    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += nhalf * P.a[i].kgroups * qb; }
+    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += nhalf * P.x[j].kgroups * qb; }
     const uint32_t stage_bytes = off;
 
     if (threadIdx.x == 0) {
@@ -398,7 +403,7 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===== loader: per (tile, quarter) one stage; one TMA box copy per source (two when hi / lo rows are apart) =====
         if (lane == 0) {
             for (int it = 0; it < n_stage_iters; ++it) {
-                const int tile = t0 + (it >> 2), q = it & 3;
+                const int tile = t0 + it / (int)per_tile, q = it % (int)per_tile;
                 const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
@@ -409,6 +414,7 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const CUtensorMap* map = is_a ? &map_a : (i - P.n_a == 0 ? &map_x0 : &map_x1);
                     const uint32_t row0 = (uint32_t)tile * (uint32_t)((is_a ? kGTileBytes : kTileBytes) / 2048) + src.slot_off / 2048;
                     const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
+                    // box = rows x 256 elements: u16 elements (512 B, 32 points) in three-term mode, u32 (1024 B, 64 points) in fp16 mode
                     tma_load_2d(d, map, q * 256, row0, bar_full + 8 * s);                 // box rows = 2*kgroups or kgroups
                     if (nhalf == 2 && src.lo_off != src.kgroups * 2048)
                         tma_load_2d(d + src.kgroups * kQuarter, map, q * 256, row0 + src.lo_off / 2048, bar_full + 8 * s);
@@ -424,17 +430,17 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 tc_fence_after();
                 const uint32_t st = sbase + s * stage_stride;
 #pragma unroll 1
-                for (uint32_t ks = 0; ks < 2; ++ks) {
+                for (uint32_t ks = 0; ks < ksteps; ++ks) {
                     uint32_t col = 0;
                     for (int i = 0; i < P.n_a; ++i) {
-                        const uint32_t halves = P.a[i].kgroups / 16, a_lo_off = P.a[i].kgroups * kQuarter;
+                        const uint32_t halves = P.a[i].kgroups / 16, a_lo_off = P.a[i].kgroups * qb;
                         for (uint32_t h = 0; h < halves; ++h) {
-                            const uint32_t a_hi = st + a_off[i] + h * 16 * kQuarter + ks * 256;
-                            const uint64_t ah = smem_desc_any(a_hi, 128, kQuarter), al = smem_desc_any(a_hi + a_lo_off, 128, kQuarter);
+                            const uint32_t a_hi = st + a_off[i] + h * 16 * qb + ks * 256;
+                            const uint64_t ah = smem_desc_any(a_hi, 128, qb), al = smem_desc_any(a_hi + a_lo_off, 128, qb);
                             for (int j = 0; j < P.n_x; ++j) {
                                 const uint32_t N = P.x[j].kgroups * 8;
                                 const uint32_t x_hi = st + x_off[j] + ks * 256;
-                                const uint64_t xh = smem_desc_any(x_hi, 128, kQuarter), xl = smem_desc_any(x_hi + P.x[j].kgroups * kQuarter, 128, kQuarter);
+                                const uint64_t xh = smem_desc_any(x_hi, 128, qb), xl = smem_desc_any(x_hi + P.x[j].kgroups * qb, 128, qb);
                                 const uint32_t idesc = instr_desc_mn(128, N);
                                 umma_f16(tmem + col, ah, xh, idesc, (it == 0 && ks == 0) ? 0u : 1u);
                                 if (nhalf == 2) { umma_f16(tmem + col, ah, xl, idesc, 1u); umma_f16(tmem + col, al, xh, idesc, 1u); }
@@ -466,11 +472,13 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     for (uint32_t g = 0; g < 4; ++g) {
                         if (g < per_warp) {
                             const uint32_t kg = warp * per_warp + g;
-                            const uint32_t addr = st + a_off[i] + kg * kQuarter + lane * 16;
+                            const uint32_t addr = st + a_off[i] + kg * qb + lane * 16;
                             uint4 hi, lo = make_uint4(0u, 0u, 0u, 0u);
                             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(addr));
-                            if (nhalf == 2)
-                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * kQuarter));
+                            if (nhalf == 2)      // three-term: the lo halves of the same 32 points; fp16: the second 32 points of the row
+                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * qb));
+                            else
+                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + 512));
                             const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -656,7 +664,7 @@ using namespace cnerf;
 namespace cnerf {
 int bwd_stream3_blocks() { return kC3NumBlocks; }
 int pack_bwd_stream3(const RawParams& p, uint8_t* stream, cudaStream_t st) {
-    pack_bwd_weights3_kernel<<<kC3NumBlocks, 256, 0, st>>>(p, stream);
+    pack_bwd_weights3_kernel<<<dim3(kC3NumBlocks, kWeightReplicas), 256, 0, st>>>(p, stream);
     CNERF_LAUNCH_CHECK("pack_bwd_weights3_kernel");
     return CNERF_OK;
 }
@@ -680,14 +688,15 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 // record buffer as [rows][1024 x u16] (2048-byte k-group rows); box = box_rows x 256 u16 (one 32-point quarter)
-int make_record_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+// wide: the same rows as [512 x u32], box = box_rows x 256 u32 (two quarters = 64 points per copy; a box dimension is at most 256 elements)
+int make_record_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows, bool wide) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[2] = {1024, rows};
+    cuuint64_t gdim[2] = {wide ? 512u : 1024u, rows};
     cuuint64_t gstride[1] = {2048};
     cuuint32_t box[2] = {256, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(m, wide ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(CNERF_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -810,9 +819,10 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
     auto run_pass = [&](DwPass& P, const DwSeg* segs, int nseg, float* db0, int n0, float* db1, int n1) -> int {
         P.terms = dw_terms;
         CUtensorMap ma, mx0, mx1;
-        int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]));
-        if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]));
-        if (r == CNERF_OK) r = make_record_map(&mx1, c.a, a_rows, box_rows(P.x[P.n_x - 1]));
+        const bool wide = dw_terms == 1;
+        int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]), wide);
+        if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]), wide);
+        if (r == CNERF_OK) r = make_record_map(&mx1, c.a, a_rows, box_rows(P.x[P.n_x - 1]), wide);
         if (r != CNERF_OK) return r;
         mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(ma, mx0, mx1, P, tiles, c.dw_part + (size_t)pass * kDwPassFloats,
                                                                  c.db_part + (size_t)pass * kDbPassFloats);

@@ -42,7 +42,7 @@ pack_weights3_kernel(RawParams p, uint8_t* __restrict__ stream) {
     const Blk3 bi = block3_info(blockIdx.x);
     const float* W = p.w[bi.layer];
     const int ld = p.ld[bi.layer];
-    uint8_t* dst = stream + (size_t)blockIdx.x * kBlockBytes;
+    uint8_t* dst = stream + ((size_t)blockIdx.y * k3NumBlocks + blockIdx.x) * kBlockBytes;      // blockIdx.y: replica
     const int rows = bi.layer == 9 ? 128 : 256, kgs = bi.layer == 9 ? 4 : 2;
     for (int u = threadIdx.x; u < rows * kgs; u += 256) {
         const int n = u % rows, kg = u / rows;
@@ -85,6 +85,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     const uint32_t bar_hv = bar_eready + 8;                      //      training: views-layer output staged in SMEM
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + k3TmemSlot);
     const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+    wstream += (size_t)(blockIdx.x % kWeightReplicas) * k3NumBlocks * kBlockBytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < k3Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -403,7 +404,7 @@ mlp_fused3_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
 static int g_prof3_host = 0;        // cnerf_debug_profile3: launch the instrumented instantiation
 
 int pack_stream3(const RawParams& p, uint8_t* stream3, cudaStream_t st) {
-    pack_weights3_kernel<<<k3NumBlocks, 256, 0, st>>>(p, stream3);
+    pack_weights3_kernel<<<dim3(k3NumBlocks, kWeightReplicas), 256, 0, st>>>(p, stream3);
     CNERF_LAUNCH_CHECK("pack_weights3_kernel");
     return CNERF_OK;
 }

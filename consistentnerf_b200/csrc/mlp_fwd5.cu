@@ -9,7 +9,7 @@
 // accumulator into its next A operand, the tensor pipe runs tile Y's layer.
 //
 //   TMEM   one 256-column fp32 accumulator per tile slot (2 x 256 = all 512 columns)
-//   SMEM   per slot: A operand (K = 256, fp16, 64 KB) + encoding tile (K = 64, 16 KB);  7-stage ring of 8 KB weight units
+//   SMEM   per slot: A operand (K = 256, fp16, 64 KB) + encoding tile (K = 64, 16 KB);  8-stage ring of 8 KB weight units
 //          ([256 out-rows x 16 k] fp16: the hi halves of the three-term kernel's blocks, same stream, same order)
 //   sync   per slot: a_ready (16 warp arrivals: the slot's A operand / encoding is complete AND its accumulator has been read)
 //          and d_full (tcgen05.commit: the layer's MMAs are complete).  Layer granularity -- no k-block pipelining is needed
@@ -25,9 +25,9 @@ constexpr int k5Threads = 576;                            // 16 epilogue warps +
 constexpr uint32_t k5Act = 0;                             // + slot * 65536: 32 k-groups x 2048 B
 constexpr uint32_t k5Emb = 131072;                        // + slot * 16384: 8 k-groups
 constexpr uint32_t k5Ring = 163840;
-constexpr int k5Stages = 7;
+constexpr int k5Stages = 8;                             // power of two: the ring cursor advances with an AND, not a division
 constexpr uint32_t k5Unit = kBlockHalfBytes;              // 8 KB: the hi half of a weight block
-constexpr uint32_t k5Bars = k5Ring + k5Stages * k5Unit;   // 221184
+constexpr uint32_t k5Bars = k5Ring + k5Stages * k5Unit;   // 229376
 constexpr uint32_t k5TmemSlot = k5Bars + 192;
 constexpr uint32_t k5Smem = k5Bars + 256;
 // first unit of layer l in the block stream (mlp_blocks.cuh): 0, 4, 21, 38, 55, 72, 92, 109, 126, 143, 152
@@ -62,6 +62,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
     // tile n of this CTA = blockIdx.x + n * gridDim.x; slot s works on n = 2 it + s
     const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int n_iter = (my_tiles + 1) / 2;
+    wstream += (size_t)(blockIdx.x % kWeightReplicas) * k3NumBlocks * kBlockBytes;      // this CTA's copy of the stream (mlp_layout.cuh)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < k5Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -78,16 +79,18 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         // ===== weight loader: units in exactly the order the MMA warp consumes them =====
         if (lane == 0) {
             const uint64_t keep = l2_policy_evict_last();
-            uint32_t u = 0;
+            uint32_t st = 0, ph = 0;
             for (int it = 0; it < n_iter; ++it)
                 for (int layer = 0; layer < 10; ++layer)
                     for (int s = 0; s < 2; ++s) {
                         if (2 * it + s >= my_tiles) continue;
-                        for (int b = k5_layer_first(layer); b < k5_layer_first(layer + 1); ++b, ++u) {
-                            const uint32_t st = u % k5Stages, ph = (u / k5Stages) & 1;
+                        const uint8_t* src = wstream + (size_t)k5_layer_first(layer) * kBlockBytes;
+                        for (int nb = k5_layer_first(layer + 1) - k5_layer_first(layer); nb > 0; --nb, src += kBlockBytes) {
                             mbar_wait(bar_empty + 8 * st, ph ^ 1);
                             mbar_arrive_expect_tx(bar_full + 8 * st, k5Unit);
-                            bulk_g2s_hint(sbase + k5Ring + st * k5Unit, wstream + (size_t)b * kBlockBytes, k5Unit, bar_full + 8 * st, keep);
+                            bulk_g2s_hint(sbase + k5Ring + st * k5Unit, src, k5Unit, bar_full + 8 * st, keep);
+                            st = (st + 1) & (k5Stages - 1);
+                            ph ^= (st == 0);
                         }
                     }
         }
@@ -97,7 +100,7 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
         constexpr uint32_t kStep = 2 * (kLBO >> 4);                               // two k-groups = one K=16 step of an A tile
         const uint64_t b256 = smem_desc_any(sbase + k5Ring, 4096, 128), b128 = smem_desc(sbase + k5Ring);
         const uint64_t stream_pol = l2_policy_evict_first();
-        uint32_t u = 0;
+        uint32_t st = 0, ph = 0;                                                   // ring cursor: stage, phase parity
         long long pw_a = 0, pw_full = 0, pw_issue = 0, pw_rec = 0, p_start = kProf ? clock64() : 0;
         for (int it = 0; it < n_iter; ++it) {
 #pragma unroll 1
@@ -121,34 +124,37 @@ mlp_fused5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__
                         bulk_commit();
                     }
                     __syncwarp();
-                    const int n_emb = (layer == 0 || layer == 5) ? 4 : 0, n_act = (layer == 0 || layer == 9) ? 0 : 16;
-                    const int nb = k5_layer_first(layer + 1) - k5_layer_first(layer);
+                    // The issue loop carries as little as possible: tcgen05.mma issue is synchronous with execution, so every instruction
+                    // between two MMAs is added to the time per MMA (scripts/umma_rate.py).  One running A descriptor per segment, ring
+                    // cursor advanced with an AND.
+                    uint32_t acc = 0u;
+                    auto segment = [&](uint64_t a, int count, uint32_t a_step) {
 #pragma unroll 1
-                    for (int j = 0; j < nb; ++j, ++u) {
-                        const uint32_t st = u % k5Stages, ph = (u / k5Stages) & 1;
-                        { PROF5_T0(); mbar_wait(bar_full + 8 * st, ph); PROF5_ADD(pw_full); }
-                        tc_fence_after();
-                        PROF5_T0();
-                        if (elect_one()) {
-                            const uint32_t acc = j == 0 ? 0u : 1u;
-                            if (layer < 9) {
-                                const uint64_t b = b256 + (uint64_t)(st * (k5Unit >> 4));
-                                uint64_t a;
-                                if (j < n_emb) a = emb_d + (uint64_t)(j * kStep);
-                                else if (j < n_emb + n_act) a = act_d + (uint64_t)((j - n_emb) * kStep);
-                                else a = emb_d + 3 * kStep;                      // bias unit: encoding columns 48-63 (column 63 == 1.0)
-                                umma_f16(d, a, b, idesc256, acc);
-                            } else {                                              // views layer: [128 x 32] units, N = 128
-                                const uint64_t b = b128 + (uint64_t)(st * (k5Unit >> 4));
-                                const uint64_t a = j < 8 ? act_d + (uint64_t)(j * 2 * kStep) : emb_d;
-                                umma_f16(d, a, b, idesc128, acc);
-                                umma_f16(d, a + kStep, b + kStep, idesc128, 1u);
+                        for (int j = 0; j < count; ++j, a += a_step) {
+                            { PROF5_T0(); mbar_wait(bar_full + 8 * st, ph); PROF5_ADD(pw_full); }
+                            tc_fence_after();
+                            PROF5_T0();
+                            if (elect_one()) {
+                                if (layer < 9) {
+                                    umma_f16(d, a, b256 + (uint64_t)(st * (k5Unit >> 4)), idesc256, acc);
+                                } else {                                              // views layer: [128 x 32] units, N = 128, two K = 16 steps
+                                    const uint64_t b = b128 + (uint64_t)(st * (k5Unit >> 4));
+                                    umma_f16(d, a, b, idesc128, acc);
+                                    umma_f16(d, a + kStep, b + kStep, idesc128, 1u);
+                                }
+                                umma_commit(bar_empty + 8 * st);
                             }
-                            umma_commit(bar_empty + 8 * st);
+                            __syncwarp();
+                            acc = 1u;
+                            st = (st + 1) & (k5Stages - 1);
+                            ph ^= (st == 0);
+                            PROF5_ADD(pw_issue);
                         }
-                        __syncwarp();
-                        PROF5_ADD(pw_issue);
-                    }
+                    };
+                    if (layer == 0) segment(emb_d, 4, kStep);
+                    else if (layer == 5) { segment(emb_d, 4, kStep); segment(act_d, 16, kStep); }
+                    else if (layer < 9) { segment(act_d, 16, kStep); segment(emb_d + 3 * kStep, 1, 0); }      // bias unit: encoding columns 48-63 (column 63 == 1.0)
+                    else { segment(act_d, 8, 2 * kStep); segment(emb_d, 1, 0); }                              // feature columns, then the direction encoding
                     // training: the previous tile's views output (staged in this slot's A tile by its last epilogue) goes to the record
                     // now, behind layer 0's MMAs (which read the encoding tile only); it must have left before epilogue 0 rewrites A
                     if (kSave && layer == 0 && it > 0) {

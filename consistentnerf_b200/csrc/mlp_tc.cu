@@ -273,8 +273,8 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
     CNERF_REQUIRE(out, "cnerf_weights_create: null out");
     cnerf_weights* w = new cnerf_weights();
     cudaGetDevice(&w->device);
-    cudaError_t e = cudaMalloc(&w->stream3, (size_t)stream3_blocks() * kBlockBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd3, (size_t)bwd_stream3_blocks() * kBlockBytes);
+    cudaError_t e = cudaMalloc(&w->stream3, (size_t)kWeightReplicas * stream3_blocks() * kBlockBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&w->stream_bwd3, (size_t)kWeightReplicas * bwd_stream3_blocks() * kBlockBytes);
 #ifdef CNERF_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&w->stream4, stream4_bytes());
 #endif
