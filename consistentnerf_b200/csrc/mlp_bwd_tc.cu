@@ -334,6 +334,214 @@ mlp_bwd_data3_kernel(const uint8_t* __restrict__ wstream, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------
+// 1b. data-gradient chain with fp16 operands (chain_terms == 1): one MMA per MAC and TWO tiles in flight per SM -- the structure of
+//     the fp16 forward (mlp_fwd5.cu).  With hi halves only a G tile is 64 KB, two fit, and the MMA warp alternates between them step by
+//     step: while the epilogue warps turn tile X's accumulator into G_{L-1} (mask, clamp, fp16), the tensor pipe runs tile Y's step.
+//     SMEM: 2 x 64 KB G tiles + 8-stage ring of 8 KB weight units (the hi halves of the chain stream's blocks); TMEM: one 256-column
+//     accumulator per slot.  Per slot: a_ready (16 warp arrivals: G tile complete, accumulator read), d_full (tcgen05.commit), s_done
+//     (the tile's G0 has left shared memory).  The gradient record receives the hi halves only (dw_terms == 1).
+// ------------------------------------------------------------------------------------
+constexpr int kC5Threads = 576;
+constexpr uint32_t kC5Act = 0;                                        // + slot * 65536
+constexpr uint32_t kC5Ring = 131072;
+constexpr int kC5Stages = 8;
+constexpr uint32_t kC5Unit = kBlockHalfBytes;
+constexpr uint32_t kC5Bars = kC5Ring + kC5Stages * kC5Unit;           // 196608
+constexpr uint32_t kC5TmemSlot = kC5Bars + 192;
+constexpr uint32_t kC5Smem = kC5Bars + 256;
+
+__device__ __forceinline__ void emit_g_hi(uint32_t base, uint32_t row, uint32_t kg, const float* v) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __half2 t = __floats2half2_rn(v[2 * i], v[2 * i + 1]); h[i] = *reinterpret_cast<uint32_t*>(&t); }
+    st_shared_v4(base + kg * kLBO + row * 16, h[0], h[1], h[2], h[3]);
+}
+
+__global__ void __launch_bounds__(kC5Threads, 1)
+mlp_bwd_data5_kernel(const uint8_t* __restrict__ wstream, const float* __restrict__ misc, const float* __restrict__ d_raw,
+                     const uint8_t* __restrict__ acts, const uint32_t* __restrict__ amax_bits, int n_points,
+                     uint8_t* __restrict__ grads) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + kC5Bars, bar_empty = bar_full + 8 * kC5Stages;
+    const uint32_t bar_dfull = bar_empty + 8 * kC5Stages;       // [2]
+    const uint32_t bar_aready = bar_dfull + 16;                  // [2]  16 warp arrivals
+    const uint32_t bar_sdone = bar_aready + 16;                  // [2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kC5TmemSlot);
+    const int num_tiles = (n_points + (int)kRows - 1) / (int)kRows;
+    const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_iter = (my_tiles + 1) / 2;                       // slot s works on this CTA's tiles 2 it + s
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kC5Stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_aready + 8 * s, 16); mbar_init(bar_sdone + 8 * s, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(sbase + kC5TmemSlot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // ===== weight loader: the hi half of every block, in the order the MMA warp consumes them =====
+        if (lane == 0) {
+            const uint64_t keep = l2_policy_evict_last();
+            uint32_t st = 0, ph = 0;
+            for (int it = 0; it < n_iter; ++it)
+                for (int m = 0; m < 9; ++m)
+                    for (int s = 0; s < 2; ++s) {
+                        if (2 * it + s >= my_tiles) continue;
+                        const uint8_t* src = wstream + (size_t)(m == 0 ? 0 : 8 + (m - 1) * 16) * kBlockBytes;
+                        for (int nb = m == 0 ? 8 : 16; nb > 0; --nb, src += kBlockBytes) {
+                            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                            mbar_arrive_expect_tx(bar_full + 8 * st, kC5Unit);
+                            bulk_g2s_hint(sbase + kC5Ring + st * kC5Unit, src, kC5Unit, bar_full + 8 * st, keep);
+                            st = (st + 1) & (kC5Stages - 1);
+                            ph ^= (st == 0);
+                        }
+                    }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer: alternates between the two slots step by step =====
+        constexpr uint32_t idesc = instr_desc(128, 256);
+        constexpr uint32_t kStep = 2 * (kLBO >> 4);
+        const uint64_t b256 = smem_desc_any(sbase + kC5Ring, 4096, 128);
+        const uint64_t stream_pol = l2_policy_evict_first();
+        uint32_t st = 0, ph = 0;
+        for (int it = 0; it < n_iter; ++it) {
+#pragma unroll 1
+            for (int p = 0; p < 10; ++p) {
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const int n = 2 * it + s;
+                    if (n >= my_tiles) continue;
+                    const int tile = (int)blockIdx.x + n * (int)gridDim.x;
+                    const uint32_t act = sbase + kC5Act + (uint32_t)s * 65536;
+                    const uint32_t d = tmem + (uint32_t)s * 256;
+                    mbar_wait(bar_aready + 8 * s, (uint32_t)(it * 10 + p) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {      // G_{9-p} of this tile is final: stream it to the gradient record (hi halves)
+                        bulk_s2g_hint(grads + (size_t)tile * kGTileBytes + g_slot(9 - p), act, p == 0 ? 32768u : 65536u, stream_pol);
+                        bulk_commit();
+                    }
+                    __syncwarp();
+                    if (p < 9) {
+                        uint64_t a = smem_desc(act);
+                        uint32_t acc = 0u;
+#pragma unroll 1
+                        for (int j = p == 0 ? 8 : 16; j > 0; --j, a += kStep) {
+                            mbar_wait(bar_full + 8 * st, ph);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                umma_f16(d, a, b256 + (uint64_t)(st * (kC5Unit >> 4)), idesc, acc);
+                                umma_commit(bar_empty + 8 * st);
+                            }
+                            __syncwarp();
+                            acc = 1u;
+                            st = (st + 1) & (kC5Stages - 1);
+                            ph ^= (st == 0);
+                        }
+                        if (elect_one()) {
+                            bulk_wait_read0();                      // the epilogue overwrites the G tile once it sees this step done
+                            umma_commit(bar_dfull + 8 * s);
+                        }
+                    } else if (elect_one()) {                       // G0 has no consumer here: release the slot to the next tile's prologue
+                        bulk_wait_read0();
+                        mbar_arrive(bar_sdone + 8 * s);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (elect_one()) bulk_wait0();
+        __syncwarp();
+    } else {
+        // ===== prologue + epilogue warps: thread = (row, q-lane, p); per 32-column k-block it owns columns 8p..8p+7; both slots in turn =====
+        const int q = warp & 3, p = warp >> 2;
+        const uint32_t row = (uint32_t)(q * 32 + lane);
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        const float scale = grad_scale(amax_bits);
+        float4 dr0 = make_float4(0.f, 0.f, 0.f, 0.f), dr1 = dr0;      // scaled d_raw row of the tile in slot 0 / 1
+        for (int it = 0; it < n_iter; ++it) {
+#pragma unroll 1
+            for (int ph10 = 0; ph10 < 10; ++ph10) {
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const int n = 2 * it + s;
+                    if (n >= my_tiles) continue;
+                    const int tile = (int)blockIdx.x + n * (int)gridDim.x;
+                    const int grow = tile * (int)kRows + (int)row;
+                    const uint8_t* arec = acts + (size_t)tile * kTileBytes;
+                    const uint32_t ab = sbase + kC5Act + (uint32_t)s * 65536;
+                    if (ph10 == 0) {
+                        // G9 = (d_rgb W_rgb) * [hv > 0]: K = 128, four k-blocks of 32 columns
+                        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (grow < n_points) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + grow);
+                        dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+                        if (s) dr1 = dr; else dr0 = dr;
+                        const uint4 mrow = __ldg(reinterpret_cast<const uint4*>(arec + kSlotM + 32768 + row * 16));
+                        const uint32_t mword[4] = {mrow.x, mrow.y, mrow.z, mrow.w};
+                        if (it > 0) mbar_wait(bar_sdone + 8 * s, (uint32_t)(it - 1) & 1);      // the slot's previous G0 has left the tile
+#pragma unroll
+                        for (uint32_t kb = 0; kb < 4; ++kb) {
+                            const uint32_t kg = kb * 4 + (uint32_t)p, c = kg * 8;
+                            const uint32_t mbits = mword[kb] >> (8 * (uint32_t)p);
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float gsum = dr.x * __ldg(misc + kMiscRgbW + c + j) + dr.y * __ldg(misc + kMiscRgbW + 128 + c + j) +
+                                                   dr.z * __ldg(misc + kMiscRgbW + 256 + c + j);
+                                v[j] = ((mbits >> j) & 1u) ? clamp_h(gsum) : 0.f;
+                            }
+                            emit_g_hi(ab, row, kg, v);
+                        }
+                    } else {
+                        const int m = ph10 - 1, L = 9 - m;               // accumulator = gradient w.r.t. the input of layer L = G_{L-1} before masking
+                        const float drw = s ? dr1.w : dr0.w;
+                        uint2 mk8 = make_uint2(0u, 0u);                    // ReLU sign bits of h_{L-1}: this thread's eight bytes (k-blocks 0-3 | 4-7)
+                        if (L != 9) mk8 = __ldg(reinterpret_cast<const uint2*>(arec + kSlotM + (size_t)(L - 1) * 4096 + (size_t)p * 1024 + row * 8));
+                        mbar_wait(bar_dfull + 8 * s, (uint32_t)(it * 9 + m) & 1);
+                        tc_fence_after();
+                        const uint32_t dcol = t_lane + (uint32_t)s * 256 + (uint32_t)p * 8;
+#pragma unroll
+                        for (uint32_t half = 0; half < 2; ++half) {
+                            float v[32];
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < 4; ++k4) tmem_ld8g(dcol + (half * 4 + k4) * 32, v + 8 * k4);
+                            tmem_ld_wait();
+                            const uint32_t mw = half == 0 ? mk8.x : mk8.y;
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                                const uint32_t kg = (half * 4 + k4) * 4 + (uint32_t)p, c = kg * 8;
+                                float* w = v + 8 * k4;
+                                if (L == 8) {                             // + d_sigma * alpha_linear.weight
+                                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c)), a1 = __ldg(reinterpret_cast<const float4*>(misc + kMiscAlphaW + c + 4));
+                                    w[0] = fmaf(drw, a0.x, w[0]); w[1] = fmaf(drw, a0.y, w[1]); w[2] = fmaf(drw, a0.z, w[2]); w[3] = fmaf(drw, a0.w, w[3]);
+                                    w[4] = fmaf(drw, a1.x, w[4]); w[5] = fmaf(drw, a1.y, w[5]); w[6] = fmaf(drw, a1.z, w[6]); w[7] = fmaf(drw, a1.w, w[7]);
+                                }
+                                const uint32_t mb = L != 9 ? (mw >> (8 * k4)) : 0xffu;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) w[j] = ((mb >> j) & 1u) ? clamp_h(w[j]) : 0.f;
+                                emit_g_hi(ab, row, kg, w);
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_aready + 8 * s);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------
 // 2. weight gradients: D[n_out, k_in] = sum_p G[p, n_out] X[p, k_in]
 // ------------------------------------------------------------------------------------
 struct DwSrc { uint32_t slot_off, kgroups, lo_off; };        // hi k-groups at slot_off, lo k-groups at slot_off + lo_off
@@ -713,6 +921,7 @@ int bwd_ctx(const void* acts, void* grads_rec, int n_points, void* workspace, vo
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data3_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_data5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5Smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(mlp_bwd kernels)");
         attr_set = true;
@@ -767,7 +976,11 @@ extern "C" int cnerf_mlp_bwd_data(const cnerf_weights* w, const float* d_raw, co
     absmax_kernel<<<kNumSMs, 256, 0, c.st>>>(d_raw, (int64_t)n_points * 4, c.amax);
     CNERF_LAUNCH_CHECK("absmax_kernel");
 #define CNERF_CHAIN(P, T, L) mlp_bwd_data3_kernel<P, T, L><<<c.grid, kC3Threads, kC3Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g)
-    if (chain_terms == 1) { if (g_profc_host) CNERF_CHAIN(true, 1, false); else CNERF_CHAIN(false, 1, false); }
+    // fp16 chain: the two-tile kernel; CNERF_CHAIN1=single (or the phase profile) keeps the single-tile one-term instantiation
+    static const bool single1 = [] { const char* ev = getenv("CNERF_CHAIN1"); return ev && ev[0] == 's'; }();
+    if (chain_terms == 1 && !g_profc_host && !single1)
+        mlp_bwd_data5_kernel<<<c.grid, kC5Threads, kC5Smem, c.st>>>(w->stream_bwd3, w->misc, d_raw, c.a, c.amax, n_points, c.g);
+    else if (chain_terms == 1) { if (g_profc_host) CNERF_CHAIN(true, 1, false); else CNERF_CHAIN(false, 1, false); }
     else if (dw_terms == 1) CNERF_CHAIN(false, 3, false);
     else if (g_profc_host) CNERF_CHAIN(true, 3, true);
     else CNERF_CHAIN(false, 3, true);

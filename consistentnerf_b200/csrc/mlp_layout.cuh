@@ -6,10 +6,10 @@
 namespace cnerf {
 
 constexpr int kNumLayers = 10;                  // 0-7 pts_linears, 8 feature_linear, 9 views_linears.0
-// Every CTA streams the same 2.4 MB of weight blocks in the same order at roughly the same time, i.e. 148 SMs hammer the same few
-// L2 slices while the others idle.  The packed streams are therefore kept in kWeightReplicas copies (L2 resident: 8 x 2.4 MB of
-// 126 MB) and CTA b reads copy b % kWeightReplicas.
-constexpr int kWeightReplicas = 8;
+// Copies of the packed weight streams (CTA b reads copy b % kWeightReplicas).  Measured with 8 copies (profiles/r2e_*): the wait for
+// weight blocks did not change (28.3k cycles per tile in mlp_fwd5 either way), i.e. the 148 SMs streaming the same blocks at the same
+// time is NOT an L2 hot-spot problem, and the larger L2 footprint cost the three-term kernels 5-10 %.  Hence one copy.
+constexpr int kWeightReplicas = 1;
 constexpr uint32_t kBlockBytes = 16384;
 constexpr uint32_t kBlockHalfBytes = 8192;
 

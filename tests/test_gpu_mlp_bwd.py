@@ -253,3 +253,30 @@ def test_autograd_path_matches_cuda_core_backward(setup):
     cn.ops.MLP_BWD = "tc"
     for k in out["tc"]:
         assert rel_err(out["tc"][k], out["simt"][k]) < 2e-5, k
+
+
+def test_two_tile_kernels_many_tiles_per_cta(setup):
+    """fp16 forward (mlp_fwd5) and fp16 chain (mlp_bwd_data5) keep two tiles in flight per CTA: 40 000 points = 313 tiles over 148
+    CTAs (some CTAs get 3 tiles, the others 2: both slots, odd counts, ragged last tile) against the three-term path on the GPU."""
+    cn = setup["cn"]
+    packed, P = setup["packed"], setup["P"]
+    gen = torch.Generator().manual_seed(11)
+    n, S = 625, 64
+    pts = (torch.randn(n, S, 3, generator=gen) * 1.5).to(DEV)
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(DEV)
+    d_raw = (torch.randn(n * S, 4, generator=gen) * 1e-6).to(DEV)
+    raw3, acts3 = cn.ops.fused_mlp_forward_train(packed, pts, vd, dw_terms=3, fwd_terms=3)
+    g3 = cn.ops.fused_mlp_backward(packed, P, acts3, d_raw, n * S, terms=(3, 3))
+    del acts3
+    for ft in (3, 1):
+        raw1, acts1 = cn.ops.fused_mlp_forward_train(packed, pts, vd, dw_terms=1, fwd_terms=ft)
+        assert rel_err(raw1, raw3) < (1e-3 if ft == 1 else 1e-7)
+        g1 = cn.ops.fused_mlp_backward(packed, P, acts1, d_raw, n * S, terms=(1, 1))
+        a = torch.cat([g1[k].double().reshape(-1) for k in sorted(g1)])
+        b = torch.cat([g3[k].double().reshape(-1) for k in sorted(g3)])
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        print(f"fwd_terms={ft}: fp16 chain + dW vs three-term, 40 000 points: 1 - cos = {1 - cos:.2e}")
+        assert cos > (1.0 - 2e-3 if ft == 1 else 1.0 - 1e-5), (ft, cos)
+        again = cn.ops.fused_mlp_backward(packed, P, acts1, d_raw, n * S, terms=(1, 1))
+        assert all(torch.equal(again[k], g1[k]) for k in g1)                    # deterministic
+        del acts1
