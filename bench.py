@@ -539,8 +539,8 @@ def quality_record(args):
     root = "/tmp/cnerf_bench_twin"
     env = {"CNERF_FWD_PRECISION": ops.forward_precision(), "CNERF_GRAD_PRECISION": ops.grad_precision()}
     t0 = time.time()
-    res = _twin_cli(["twin", "--kind", "blender", "--root", root, "--iters", str(args.quality_iters), "--res", "200", "--eval-views", "4"], 900, env=env)
-    out = {"what": f"UNMODIFIED run_nerf.py train() x {args.quality_iters} iters (N_rand 4096, 64 + 128 samples, 3 views 200x200, white bkgd) -- reference "
+    res = _twin_cli(["twin", "--kind", "blender", "--root", root, "--iters", str(args.quality_iters), "--res", "200", "--eval-views", "4", "--train-views", "8"], 900, env=env)
+    out = {"what": f"UNMODIFIED run_nerf.py train() x {args.quality_iters} iters (N_rand 4096, 64 + 128 samples, 8 training views 200x200, white bkgd) -- reference "
                    "GPU eager vs this package through consistentnerf_b200.dropin -- PSNR on 4 held-out views; live, one seed (the seed-to-seed "
                    "spread of either arm is in committed_study)",
            "seconds": time.time() - t0, "committed_study": committed}

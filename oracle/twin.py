@@ -189,16 +189,17 @@ def make_dtu(root: str, seed: int = 0, scan: str = "scan114", n_val_render: int 
     return {"kind": "dtu", "root": root, "config": cfg, "H": H, "W": W, "focal": focal, "near": near, "far": far, "scan": scan}
 
 
-def make_scene(kind: str, root: str, res: int = 400, seed: int = 0) -> dict:
+def make_scene(kind: str, root: str, res: int = 400, seed: int = 0, n_train: int = 3) -> dict:
     os.makedirs(root, exist_ok=True)
     meta_path = os.path.join(root, f"scene_{kind}.json")
     if os.path.exists(meta_path):
         return json.load(open(meta_path))
     t0 = time.time()
     if kind == "blender":
-        meta = make_blender(root, res=res, seed=seed)
+        meta = make_blender(root, res=res, seed=seed, n_train=n_train)
+        meta["n_train"] = n_train
     elif kind == "blender_view":
-        meta = make_blender(root, res=res, seed=seed, view_script=True)
+        meta = make_blender(root, res=res, seed=seed, view_script=True, n_train=n_train)
         meta["kind"] = "blender_view"
     elif kind == "dtu":
         meta = make_dtu(root, seed=seed)
@@ -349,9 +350,10 @@ def run_arm_subprocess(arm, kind, root, iters, seed=0, eval_views=2, eval_res_di
     return json.load(open(out))
 
 
-def twin(kind, root, iters, seed=0, eval_views=2, eval_res_div=1, res=400, env_repo=None, timeout=1800, arms=("ref", "repo"), extra_args=()):
+def twin(kind, root, iters, seed=0, eval_views=2, eval_res_div=1, res=400, env_repo=None, timeout=1800, arms=("ref", "repo"), extra_args=(),
+         n_train=3):
     """Scene + both arms; -> {"psnr_repo", "psnr_ref", "delta_db", "ref": {...}, "repo": {...}}."""
-    make_scene(kind, root, res=res, seed=seed)
+    make_scene(kind, root, res=res, seed=seed, n_train=n_train)
     out = {"kind": kind, "script": SCRIPT_OF[kind] + ".py", "iters": iters, "res": res}
     for arm in arms:
         out[arm] = run_arm_subprocess(arm, kind, root, iters, seed, eval_views, eval_res_div, env=env_repo if arm == "repo" else None, timeout=timeout,
@@ -437,6 +439,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--extra", action="append", default=[])
     ap.add_argument("--arms", default="ref,repo")
+    ap.add_argument("--train-views", type=int, default=3)
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
@@ -444,11 +447,11 @@ def main():
     ap.add_argument("--device", default="cuda")
     a = ap.parse_args()
     if a.cmd == "make":
-        res = make_scene(a.kind, a.root, res=a.res, seed=a.seed)
+        res = make_scene(a.kind, a.root, res=a.res, seed=a.seed, n_train=a.train_views)
     elif a.cmd == "run":
         res = run_arm(a.arm, a.kind, a.root, a.iters, a.seed, a.eval_views, a.eval_res_div, extra_args=a.extra, device=a.device)
     elif a.cmd == "twin":
-        res = twin(a.kind, a.root, a.iters, a.seed, a.eval_views, a.eval_res_div, res=a.res, extra_args=a.extra, arms=tuple(a.arms.split(",")))
+        res = twin(a.kind, a.root, a.iters, a.seed, a.eval_views, a.eval_res_div, res=a.res, extra_args=a.extra, arms=tuple(a.arms.split(",")), n_train=a.train_views)
     else:
         res = reference_workload_a(a.device, a.rays, a.steps, a.warmup, a.mode)
     text = json.dumps(res)

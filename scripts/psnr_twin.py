@@ -28,8 +28,9 @@ def main():
     ap.add_argument("--out", default="gpurun_out/psnr_twin.json")
     ap.add_argument("--repo-modes", nargs="+", default=["split:split", "fp16:fp16"], help="forward:grad precision pairs of the drop-in arm")
     ap.add_argument("--kind", default="blender")
+    ap.add_argument("--train-views", type=int, default=3)
     a = ap.parse_args()
-    twin.make_scene(a.kind, a.root, res=a.res, seed=0)
+    twin.make_scene(a.kind, a.root, res=a.res, seed=0, n_train=a.train_views)
     runs = {"ref": []}
     t0 = time.time()
     for seed in a.seeds:
@@ -50,7 +51,7 @@ def main():
         return {"n": len(v), "mean": statistics.fmean(v) if v else None, "std": statistics.stdev(v) if len(v) > 1 else None,
                 "min": min(v) if v else None, "max": max(v) if v else None,
                 "train_ms_per_iter": statistics.fmean([r["train_ms_per_iter"] for r in rows if r.get("train_ms_per_iter")]) if v else None}
-    summary = {"what": f"UNMODIFIED run_nerf.py train() x {a.iters} iters on one synthetic {a.kind} scene ({a.res}x{a.res}, 3 training views, N_rand 4096, 64 + 128 "
+    summary = {"what": f"UNMODIFIED run_nerf.py train() x {a.iters} iters on one synthetic {a.kind} scene ({a.res}x{a.res}, {a.train_views} training views, N_rand 4096, 64 + 128 "
                        f"samples), held-out PSNR over {a.eval_views} views, seeds {a.seeds}; ref = PyTorch eager on the same GPU, the other arms = "
                        "consistentnerf_b200.dropin with forward:gradient precision as named",
                "arms": {k: stats(v) for k, v in runs.items()}}
