@@ -107,7 +107,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
-LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 3, "cnerf_mlp_bwd": 16, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 12, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 3, "cnerf_mlp_bwd": 7, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 3, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
 launch_count = 0
 # name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
 event_trace = {}

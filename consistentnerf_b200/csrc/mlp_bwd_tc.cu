@@ -557,7 +557,6 @@ struct DwPass {
 };
 
 constexpr int kDwStages = 3;                                  // three-term mode; the fp16 mode runs 2 x kDwStages half-size stages
-constexpr int kDwMaxStages = 2 * kDwStages;
 constexpr uint32_t kDwStageBytes = 73728;                     // 72 KB: two 256-wide G quarters + the 64-wide encoding (hi + lo)
 constexpr uint32_t kDwBars = kDwStages * kDwStageBytes;       // 221184
 constexpr uint32_t kDwSmem = kDwBars + 128;
@@ -569,36 +568,49 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 
+// All passes of one network in ONE persistent launch: the TMA ring keeps streaming across pass boundaries (while the epilogue warps
+// drain a pass's accumulators the loader already fetches the next pass's first stages), and the per-launch prologue (TMEM
+// allocation, barrier init, tensor-map fetch, pipeline fill) is paid once instead of ten times -- the coarse network's passes
+// move only ~130 MB each in fp16 mode, where those fixed costs were a third of the pass.
+struct alignas(64) DwAll {
+    CUtensorMap map[kDwPasses][3];      // per pass: G record, X source 0, X source 1
+    DwPass P[kDwPasses];
+    int n_pass;
+};
+
+struct DwLayout { uint32_t a_off[2], x_off[2], stage_bytes, nhalf, qb, ksteps, per_tile; };
+__device__ __forceinline__ DwLayout dw_layout(const DwPass& P) {
+    // three-term mode: a stage holds 32 points of every source as [hi | lo] k-group rows of 512 B; fp16 mode: 64 points of the
+    // hi halves as rows of 1024 B (the same stage size: half the barrier hand-shakes per byte)
+    DwLayout L;
+    L.nhalf = P.terms == 1 ? 1u : 2u;
+    L.qb = P.terms == 1 ? 2 * kQuarter : kQuarter;
+    L.ksteps = L.qb / 256;
+    L.per_tile = 128 * 16 / L.qb;
+    uint32_t off = 0;
+    for (int i = 0; i < 2; ++i) { L.a_off[i] = off; if (i < P.n_a) off += L.nhalf * P.a[i].kgroups * L.qb; }
+    for (int j = 0; j < 2; ++j) { L.x_off[j] = off; if (j < P.n_x) off += L.nhalf * P.x[j].kgroups * L.qb; }
+    L.stage_bytes = off;
+    return L;
+}
+
 __global__ void __launch_bounds__(kDwThreads, 1)
-mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x0,
-                      const __grid_constant__ CUtensorMap map_x1, DwPass P, int num_tiles,
-                      float* __restrict__ dw_part, float* __restrict__ db_part) {
+mlp_bwd_weight_kernel(const __grid_constant__ DwAll A, int num_tiles, float* __restrict__ dw_part_all, float* __restrict__ db_part_all) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwMaxStages, bar_acc = bar_empty + 8 * kDwMaxStages;
+    const uint32_t bar_full = sbase + kDwBars, bar_empty = bar_full + 8 * kDwStages, bar_acc = bar_empty + 8 * kDwStages;
+    const uint32_t bar_drained = bar_acc + 8;                    // 8 warp arrivals: the pass's accumulators have left tensor memory
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kDwBars + 112);
-    // three-term mode: a stage holds 32 points of every source as [hi | lo] k-group rows of 512 B; fp16 mode: 64 points of the
-    // hi halves as rows of 1024 B (the same stage size: half the barrier hand-shakes per byte)
-    const uint32_t nhalf = P.terms == 1 ? 1u : 2u;                          // operand halves per source in a stage
-    const uint32_t qb = P.terms == 1 ? 2 * kQuarter : kQuarter;             // bytes of one k-group row in a stage
-    const uint32_t ksteps = qb / 256, per_tile = 128 * 16 / qb;             // K = 16 MMA steps per stage, stages per 128-point tile
-    const uint32_t n_stages = kDwStages, stage_stride = kDwStageBytes;
 
     // contiguous tile range of this CTA
     const int per = num_tiles / gridDim.x, rem = num_tiles % gridDim.x;
     const int t0 = blockIdx.x * per + min((int)blockIdx.x, rem), t1 = t0 + per + ((int)blockIdx.x < rem ? 1 : 0);
-    const int n_stage_iters = (t1 - t0) * (P.terms == 1 ? 2 : 4);
-
-    // stage map: A sources then X sources, each [hi kgroups*512 | lo kgroups*512]
-    uint32_t a_off[2], x_off[2], off = 0;
-    for (int i = 0; i < P.n_a; ++i) { a_off[i] = off; off += nhalf * P.a[i].kgroups * qb; }
-    for (int j = 0; j < P.n_x; ++j) { x_off[j] = off; off += nhalf * P.x[j].kgroups * qb; }
-    const uint32_t stage_bytes = off;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kDwMaxStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 9); }
+        for (int s = 0; s < kDwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 9); }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_drained, 8);
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(sbase + kDwBars + 112, 512);
@@ -608,138 +620,162 @@ mlp_bwd_weight_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 8) {
-        // ===== loader: per (tile, quarter) one stage; one TMA box copy per source (two when hi / lo rows are apart) =====
+        // ===== loader: per (tile, point window) one stage; one TMA box copy per source (two when hi / lo rows are apart) =====
         if (lane == 0) {
-            for (int it = 0; it < n_stage_iters; ++it) {
-                const int tile = t0 + it / (int)per_tile, q = it % (int)per_tile;
-                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
-                const uint32_t dst0 = sbase + s * stage_stride;
-                for (int i = 0; i < P.n_a + P.n_x; ++i) {
-                    const bool is_a = i < P.n_a;
-                    const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
-                    const CUtensorMap* map = is_a ? &map_a : (i - P.n_a == 0 ? &map_x0 : &map_x1);
-                    const uint32_t row0 = (uint32_t)tile * (uint32_t)((is_a ? kGTileBytes : kTileBytes) / 2048) + src.slot_off / 2048;
-                    const uint32_t d = dst0 + (is_a ? a_off[i] : x_off[i - P.n_a]);
-                    // box = rows x 256 elements: u16 elements (512 B, 32 points) in three-term mode, u32 (1024 B, 64 points) in fp16 mode
-                    tma_load_2d(d, map, q * 256, row0, bar_full + 8 * s);                 // box rows = 2*kgroups or kgroups
-                    if (nhalf == 2 && src.lo_off != src.kgroups * 2048)
-                        tma_load_2d(d + src.kgroups * kQuarter, map, q * 256, row0 + src.lo_off / 2048, bar_full + 8 * s);
+            uint32_t s = 0, ph = 0;
+            for (int pass = 0; pass < A.n_pass; ++pass) {
+                const DwPass& P = A.P[pass];
+                const DwLayout L = dw_layout(P);
+                const int n_stage_iters = (t1 - t0) * (int)L.per_tile;
+                for (int it = 0; it < n_stage_iters; ++it) {
+                    const int tile = t0 + it / (int)L.per_tile, q = it % (int)L.per_tile;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, L.stage_bytes);
+                    const uint32_t dst0 = sbase + s * kDwStageBytes;
+                    for (int i = 0; i < P.n_a + P.n_x; ++i) {
+                        const bool is_a = i < P.n_a;
+                        const DwSrc src = is_a ? P.a[i] : P.x[i - P.n_a];
+                        const CUtensorMap* map = &A.map[pass][is_a ? 0 : 1 + (i - P.n_a)];
+                        const uint32_t row0 = (uint32_t)tile * (uint32_t)((is_a ? kGTileBytes : kTileBytes) / 2048) + src.slot_off / 2048;
+                        const uint32_t d = dst0 + (is_a ? L.a_off[i] : L.x_off[i - P.n_a]);
+                        // box = rows x 256 elements: u16 elements (512 B, 32 points) in three-term mode, u32 (1024 B, 64 points) in fp16 mode
+                        tma_load_2d(d, map, q * 256, row0, bar_full + 8 * s);                 // box rows = 2*kgroups or kgroups
+                        if (L.nhalf == 2 && src.lo_off != src.kgroups * 2048)
+                            tma_load_2d(d + src.kgroups * kQuarter, map, q * 256, row0 + src.lo_off / 2048, bar_full + 8 * s);
+                    }
+                    if (++s == kDwStages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 9) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int it = 0; it < n_stage_iters; ++it) {
-                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t st = sbase + s * stage_stride;
+            uint32_t s = 0, ph = 0;
+            for (int pass = 0; pass < A.n_pass; ++pass) {
+                const DwPass& P = A.P[pass];
+                const DwLayout L = dw_layout(P);
+                const int n_stage_iters = (t1 - t0) * (int)L.per_tile;
+                if (pass > 0) { mbar_wait(bar_drained, (uint32_t)(pass - 1) & 1); tc_fence_after(); }      // tensor memory is free again
+                for (int it = 0; it < n_stage_iters; ++it) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = sbase + s * kDwStageBytes;
 #pragma unroll 1
-                for (uint32_t ks = 0; ks < ksteps; ++ks) {
-                    uint32_t col = 0;
-                    for (int i = 0; i < P.n_a; ++i) {
-                        const uint32_t halves = P.a[i].kgroups / 16, a_lo_off = P.a[i].kgroups * qb;
-                        for (uint32_t h = 0; h < halves; ++h) {
-                            const uint32_t a_hi = st + a_off[i] + h * 16 * qb + ks * 256;
-                            const uint64_t ah = smem_desc_any(a_hi, 128, qb), al = smem_desc_any(a_hi + a_lo_off, 128, qb);
-                            for (int j = 0; j < P.n_x; ++j) {
-                                const uint32_t N = P.x[j].kgroups * 8;
-                                const uint32_t x_hi = st + x_off[j] + ks * 256;
-                                const uint64_t xh = smem_desc_any(x_hi, 128, qb), xl = smem_desc_any(x_hi + P.x[j].kgroups * qb, 128, qb);
-                                const uint32_t idesc = instr_desc_mn(128, N);
-                                umma_f16(tmem + col, ah, xh, idesc, (it == 0 && ks == 0) ? 0u : 1u);
-                                if (nhalf == 2) { umma_f16(tmem + col, ah, xl, idesc, 1u); umma_f16(tmem + col, al, xh, idesc, 1u); }
-                                col += N;
+                    for (uint32_t ks = 0; ks < L.ksteps; ++ks) {
+                        uint32_t col = 0;
+                        for (int i = 0; i < P.n_a; ++i) {
+                            const uint32_t halves = P.a[i].kgroups / 16, a_lo_off = P.a[i].kgroups * L.qb;
+                            for (uint32_t h = 0; h < halves; ++h) {
+                                const uint32_t a_hi = st + L.a_off[i] + h * 16 * L.qb + ks * 256;
+                                const uint64_t ah = smem_desc_any(a_hi, 128, L.qb), al = smem_desc_any(a_hi + a_lo_off, 128, L.qb);
+                                for (int j = 0; j < P.n_x; ++j) {
+                                    const uint32_t N = P.x[j].kgroups * 8;
+                                    const uint32_t x_hi = st + L.x_off[j] + ks * 256;
+                                    const uint64_t xh = smem_desc_any(x_hi, 128, L.qb), xl = smem_desc_any(x_hi + P.x[j].kgroups * L.qb, 128, L.qb);
+                                    const uint32_t idesc = instr_desc_mn(128, N);
+                                    umma_f16(tmem + col, ah, xh, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+                                    if (L.nhalf == 2) { umma_f16(tmem + col, ah, xl, idesc, 1u); umma_f16(tmem + col, al, xh, idesc, 1u); }
+                                    col += N;
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                    if (++s == kDwStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(bar_acc);
+            }
+        }
+    } else {
+        // ===== bias-gradient column sums (from the same SMEM tiles), then the TMEM -> partial epilogue, pass by pass =====
+        uint32_t s = 0, ph = 0;
+        for (int pass = 0; pass < A.n_pass; ++pass) {
+            const DwPass& P = A.P[pass];
+            const DwLayout L = dw_layout(P);
+            const int n_stage_iters = (t1 - t0) * (int)L.per_tile;
+            float* dw_part = dw_part_all + (size_t)pass * kDwPassFloats;
+            float* db_part = db_part_all + (size_t)pass * kDbPassFloats;
+            float acc[2][32];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
+            for (int it = 0; it < n_stage_iters; ++it) {
+                mbar_wait(bar_full + 8 * s, ph);
+                const uint32_t st = sbase + s * kDwStageBytes;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i < P.n_a && ((P.db_mask >> i) & 1)) {
+                        const uint32_t per_warp = P.a[i].kgroups / 8;       // 4 (256 wide) or 2 (128 wide)
+#pragma unroll
+                        for (uint32_t g = 0; g < 4; ++g) {
+                            if (g < per_warp) {
+                                const uint32_t kg = warp * per_warp + g;
+                                const uint32_t addr = st + L.a_off[i] + kg * L.qb + lane * 16;
+                                uint4 hi, lo = make_uint4(0u, 0u, 0u, 0u);
+                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(addr));
+                                if (L.nhalf == 2)      // three-term: the lo halves of the same 32 points; fp16: the second 32 points of the row
+                                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * L.qb));
+                                else
+                                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + 512));
+                                const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                                    float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                                    acc[i][g * 8 + 2 * e] += a.x + b.x;
+                                    acc[i][g * 8 + 2 * e + 1] += a.y + b.y;
+                                }
                             }
                         }
                     }
                 }
-                umma_commit(bar_empty + 8 * s);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+                if (++s == kDwStages) { s = 0; ph ^= 1; }
             }
-            umma_commit(bar_acc);
-        }
-    } else {
-        // ===== bias-gradient column sums (from the same SMEM tiles), then the TMEM -> partial epilogue =====
-        float acc[2][32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
-        for (int it = 0; it < n_stage_iters; ++it) {
-            const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-            mbar_wait(bar_full + 8 * s, ph);
-            const uint32_t st = sbase + s * stage_stride;
+            // bias partials: reduce over the 32 point-lanes
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (i < P.n_a && ((P.db_mask >> i) & 1)) {
-                    const uint32_t per_warp = P.a[i].kgroups / 8;       // 4 (256 wide) or 2 (128 wide)
+                    const uint32_t per_warp = P.a[i].kgroups / 8;
 #pragma unroll
-                    for (uint32_t g = 0; g < 4; ++g) {
-                        if (g < per_warp) {
-                            const uint32_t kg = warp * per_warp + g;
-                            const uint32_t addr = st + a_off[i] + kg * qb + lane * 16;
-                            uint4 hi, lo = make_uint4(0u, 0u, 0u, 0u);
-                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(addr));
-                            if (nhalf == 2)      // three-term: the lo halves of the same 32 points; fp16: the second 32 points of the row
-                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + P.a[i].kgroups * qb));
-                            else
-                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(addr + 512));
-                            const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                    for (int k = 0; k < 32; ++k) {
+                        float v = warp_sum(acc[i][k]);
+                        if (lane == 0 && (uint32_t)(k >> 3) < per_warp)
+                            db_part[((size_t)blockIdx.x * 2 + i) * 256 + (warp * per_warp + (k >> 3)) * 8 + (k & 7)] = v;
+                    }
+                }
+            }
+            // accumulators -> per-CTA partial, block by block: [block][128 rows][N]
+            mbar_wait(bar_acc, (uint32_t)pass & 1);
+            tc_fence_after();
+            float* part = dw_part + (size_t)blockIdx.x * 128 * 512;
+            const uint32_t rowq = (uint32_t)(warp & 3) * 32, row = rowq + lane;
+            uint32_t col = 0;
+            for (int i = 0; i < P.n_a; ++i)
+                for (uint32_t h = 0; h < P.a[i].kgroups / 16; ++h)
+                    for (int j = 0; j < P.n_x; ++j) {
+                        const uint32_t N = P.x[j].kgroups * 8;
+                        float* blk = part + (size_t)col * 128;                 // block base: 128 x N floats
+                        for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < N; c += 64) {
+                            float v[32];
+                            tmem_ld32(tmem + (rowq << 16) + col + c, v);
+                            tmem_ld_wait();
+                            float4* o = reinterpret_cast<float4*>(blk + (size_t)row * N + c);
+                            if (n_stage_iters == 0) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-                                float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-                                acc[i][g * 8 + 2 * e] += a.x + b.x;
-                                acc[i][g * 8 + 2 * e + 1] += a.y + b.y;
+                                for (int k = 0; k < 32; ++k) v[k] = 0.f;
                             }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         }
+                        col += N;
                     }
-                }
-            }
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            if (lane == 0) mbar_arrive(bar_drained);
         }
-        // bias partials: reduce over the 32 point-lanes
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (i < P.n_a && ((P.db_mask >> i) & 1)) {
-                const uint32_t per_warp = P.a[i].kgroups / 8;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float v = warp_sum(acc[i][k]);
-                    if (lane == 0 && (uint32_t)(k >> 3) < per_warp)
-                        db_part[((size_t)blockIdx.x * 2 + i) * 256 + (warp * per_warp + (k >> 3)) * 8 + (k & 7)] = v;
-                }
-            }
-        }
-        // accumulators -> per-CTA partial, block by block: [block][128 rows][N]
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        float* part = dw_part + (size_t)blockIdx.x * 128 * 512;
-        const uint32_t rowq = (uint32_t)(warp & 3) * 32, row = rowq + lane;
-        uint32_t col = 0;
-        for (int i = 0; i < P.n_a; ++i)
-            for (uint32_t h = 0; h < P.a[i].kgroups / 16; ++h)
-                for (int j = 0; j < P.n_x; ++j) {
-                    const uint32_t N = P.x[j].kgroups * 8;
-                    float* blk = part + (size_t)col * 128;                 // block base: 128 x N floats
-                    for (uint32_t c = (uint32_t)(warp >> 2) * 32; c < N; c += 64) {
-                        float v[32];
-                        tmem_ld32(tmem + (rowq << 16) + col + c, v);
-                        tmem_ld_wait();
-                        float4* o = reinterpret_cast<float4*>(blk + (size_t)row * N + c);
-                        if (n_stage_iters == 0) {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) v[k] = 0.f;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    }
-                    col += N;
-                }
     }
     tc_fence_before();
     __syncthreads();
@@ -1028,18 +1064,16 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
     auto box_rows = [dw_terms](const DwSrc& s) { return (dw_terms == 3 && s.lo_off == s.kgroups * 2048) ? 2 * s.kgroups : s.kgroups; };
     DwSegs all = {};
     DbSegs alldb = {};
+    static thread_local DwAll A;      // ~4.6 KB of kernel parameters: tensor maps + pass descriptors of all ten passes
     int pass = 0;
     auto run_pass = [&](DwPass& P, const DwSeg* segs, int nseg, float* db0, int n0, float* db1, int n1) -> int {
         P.terms = dw_terms;
-        CUtensorMap ma, mx0, mx1;
         const bool wide = dw_terms == 1;
-        int r = make_record_map(&ma, c.g, g_rows, box_rows(P.a[0]), wide);
-        if (r == CNERF_OK) r = make_record_map(&mx0, c.a, a_rows, box_rows(P.x[0]), wide);
-        if (r == CNERF_OK) r = make_record_map(&mx1, c.a, a_rows, box_rows(P.x[P.n_x - 1]), wide);
+        int r = make_record_map(&A.map[pass][0], c.g, g_rows, box_rows(P.a[0]), wide);
+        if (r == CNERF_OK) r = make_record_map(&A.map[pass][1], c.a, a_rows, box_rows(P.x[0]), wide);
+        if (r == CNERF_OK) r = make_record_map(&A.map[pass][2], c.a, a_rows, box_rows(P.x[P.n_x - 1]), wide);
         if (r != CNERF_OK) return r;
-        mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(ma, mx0, mx1, P, tiles, c.dw_part + (size_t)pass * kDwPassFloats,
-                                                                 c.db_part + (size_t)pass * kDbPassFloats);
-        CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
+        A.P[pass] = P;
         for (int i = 0; i < nseg; ++i) { all.s[all.n] = segs[i]; all.s[all.n].pass = pass; ++all.n; }
         if (db0) alldb.s[alldb.n++] = {db0, n0, pass, 0};
         if (db1) alldb.s[alldb.n++] = {db1, n1, pass, 1};
@@ -1068,6 +1102,9 @@ extern "C" int cnerf_mlp_bwd_weights(const void* acts, const void* grads_rec, in
         DwSeg S[2] = {{d_views_w, 283, 0, 0, 256, 0, 256, 0, 0}, {d_views_w, 283, 0, 256, 27, 128 * 256, 32, 0, 0}};
         if ((rc = run_pass(P, S, 2, d_views_b, 128, nullptr, 0)) != CNERF_OK) return rc;
     }
+    A.n_pass = pass;
+    mlp_bwd_weight_kernel<<<grid, kDwThreads, kDwSmem, st>>>(A, tiles, c.dw_part, c.db_part);
+    CNERF_LAUNCH_CHECK("mlp_bwd_weight_kernel");
     dw_reduce_kernel<<<dim3(ceil_div(128 * 256, 256), all.n), 256, 0, st>>>(all, c.dw_part, grid, c.amax, accumulate);
     CNERF_LAUNCH_CHECK("dw_reduce_kernel");
     db_reduce_kernel<<<dim3(1, alldb.n), 256, 0, st>>>(alldb, c.db_part, grid, c.amax, accumulate);

@@ -254,9 +254,10 @@ def run_arm(arm: str, kind: str, root: str, iters: int, seed: int = 0, eval_view
     script = SCRIPT_OF[kind]
     import importlib
     m = importlib.import_module(script)
-    patched = []
+    patched, originals = [], {}
     if arm == "repo":
         from consistentnerf_b200 import dropin
+        originals = {k: getattr(m, k) for k in dropin._RENDER_NAMES + dropin._MODEL_NAMES + dropin._VIEW_NAMES if hasattr(m, k)}
         patched = dropin.patch(m)
     if device == "cuda":
         torch.set_default_tensor_type("torch.cuda.FloatTensor")
@@ -327,11 +328,60 @@ def run_arm(arm: str, kind: str, root: str, iters: int, seed: int = 0, eval_view
                 gt = cv2.resize(gt, (Ww, Hh), interpolation=cv2.INTER_AREA)
             mse = float(((rgb.cpu().numpy().astype(np.float64) - gt.astype(np.float64)) ** 2).mean())
             psnrs.append(-10.0 * math.log10(mse))
+    # Render parity ON THE TRAINED WEIGHTS: the same networks, the same held-out poses, once through this package's renderer (above)
+    # and once through the reference's own functions (module globals restored for the duration), so that the precision of the
+    # forward is judged on a trained model and not only on the default-initialised workload A.
+    same_weights = None
+    if arm == "repo" and originals:
+        ours = {k: getattr(m, k) for k in originals}
+        try:
+            for k, f in originals.items():
+                setattr(m, k, f)
+            RefNeRF, ref_get_embedder = originals["NeRF"], originals["get_embedder"]
+            e_fn, in_ch = ref_get_embedder(args.multires, args.i_embed)
+            ev_fn, in_v = ref_get_embedder(args.multires_views, args.i_embed) if args.use_viewdirs else (None, 0)
+            out_ch = 5 if args.N_importance > 0 else 4
+
+            def clone(net):
+                if net is None:
+                    return None
+                r = RefNeRF(D=args.netdepth, W=args.netwidth, input_ch=in_ch, output_ch=out_ch, skips=[4], input_ch_views=in_v,
+                            use_viewdirs=args.use_viewdirs).to(m.device)
+                r.load_state_dict(net.state_dict())
+                return r
+            kw_ref = dict(render_kwargs_test)
+            kw_ref["network_fn"], kw_ref["network_fine"] = clone(render_kwargs_test["network_fn"]), clone(render_kwargs_test.get("network_fine"))
+            kw_ref["network_query_fn"] = lambda inputs, viewdirs, network_fn: m.run_network(inputs, viewdirs, network_fn, embed_fn=e_fn,
+                                                                                          embeddirs_fn=ev_fn, netchunk=args.netchunk)
+            diffs, psnr_r, psnr_o = [], [], []
+            with torch.no_grad():
+                for v in range(min(2, len(poses))):
+                    c2w = torch.Tensor(poses[v][:3, :4])
+                    ref_rgb = m.render(H, W, K, chunk=args.chunk, c2w=c2w, **kw_ref)[0].cpu().numpy().astype(np.float64)
+                    for k, f in ours.items():
+                        setattr(m, k, f)
+                    our_rgb = m.render(H, W, K, chunk=args.chunk, c2w=c2w, **render_kwargs_test)[0].cpu().numpy().astype(np.float64)
+                    for k, f in originals.items():
+                        setattr(m, k, f)
+                    gt = images[v].astype(np.float64)
+                    diffs.append(float(np.abs(ref_rgb - our_rgb).max()))
+                    psnr_r.append(-10.0 * math.log10(((ref_rgb - gt) ** 2).mean()))
+                    psnr_o.append(-10.0 * math.log10(((our_rgb - gt) ** 2).mean()))
+                    mse_ro = float(((ref_rgb - our_rgb) ** 2).mean())
+            same_weights = {"views": len(diffs), "max_abs_rgb_diff": max(diffs), "psnr_reference_renderer": float(np.mean(psnr_r)),
+                            "psnr_this_renderer": float(np.mean(psnr_o)), "delta_db": float(np.mean(psnr_o) - np.mean(psnr_r)),
+                            "psnr_between_renderers": -10.0 * math.log10(max(mse_ro, 1e-30))}
+        except Exception as e:      # report, do not fail the arm
+            same_weights = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            for k, f in ours.items():
+                setattr(m, k, f)
     nr = min(eval_views, len(poses)) * (H // eval_res_div) * (W // eval_res_div)
     res = {"arm": arm, "script": script + ".py", "kind": kind, "iters": iters, "patched": patched, "psnr_views": psnrs,
            "psnr": float(np.mean(psnrs)), "train_ms_per_iter": ms_iter, "train_rays_per_s": (1e3 * args.N_rand / ms_iter) if ms_iter else None, "device": device, "args": extra_args,
            "train_seconds": t_train, "render_rays_per_s": nr / t_render, "eval_views": len(psnrs), "eval_hw": [H // eval_res_div, W // eval_res_div],
-           "checkpoints": ckpts, "grad_precision": os.environ.get("CNERF_GRAD_PRECISION", "default") if arm == "repo" else None}
+           "checkpoints": ckpts, "same_weights_render_parity": same_weights,
+           "fwd_precision": os.environ.get("CNERF_FWD_PRECISION", "default") if arm == "repo" else None, "grad_precision": os.environ.get("CNERF_GRAD_PRECISION", "default") if arm == "repo" else None}
     return res
 
 

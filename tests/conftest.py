@@ -25,7 +25,7 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(autouse=True)
+@pytest.fixture(autouse=True, scope="session")
 def _three_term_precision_unless_a_test_says_otherwise():
     """The parity tests against the fp64 oracle / the reference's golden vectors pin the fp32-equivalent (three-term) arithmetic;
     the fp16-operand modes have their own tests (test_gpu_fwd_fp16.py, test_gpu_mlp_bwd.py) which select them explicitly.
