@@ -353,7 +353,7 @@ def run_arm(arm: str, kind: str, root: str, iters: int, seed: int = 0, eval_view
             kw_ref["network_fn"], kw_ref["network_fine"] = clone(render_kwargs_test["network_fn"]), clone(render_kwargs_test.get("network_fine"))
             kw_ref["network_query_fn"] = lambda inputs, viewdirs, network_fn: m.run_network(inputs, viewdirs, network_fn, embed_fn=e_fn,
                                                                                           embeddirs_fn=ev_fn, netchunk=args.netchunk)
-            diffs, psnr_r, psnr_o = [], [], []
+            diffs, psnr_r, psnr_o, all_abs = [], [], [], []
             with torch.no_grad():
                 for v in range(min(2, len(poses))):
                     c2w = torch.Tensor(poses[v][:3, :4])
@@ -365,10 +365,15 @@ def run_arm(arm: str, kind: str, root: str, iters: int, seed: int = 0, eval_view
                         setattr(m, k, f)
                     gt = images[v].astype(np.float64)
                     diffs.append(float(np.abs(ref_rgb - our_rgb).max()))
+                    all_abs.append(np.abs(ref_rgb - our_rgb).max(-1).reshape(-1))            # per pixel: worst channel
                     psnr_r.append(-10.0 * math.log10(((ref_rgb - gt) ** 2).mean()))
                     psnr_o.append(-10.0 * math.log10(((our_rgb - gt) ** 2).mean()))
                     mse_ro = float(((ref_rgb - our_rgb) ** 2).mean())
-            same_weights = {"views": len(diffs), "max_abs_rgb_diff": max(diffs), "psnr_reference_renderer": float(np.mean(psnr_r)),
+            px = np.concatenate(all_abs)
+            same_weights = {"views": len(diffs), "pixels": int(px.size), "max_abs_rgb_diff": max(diffs),
+                            "abs_diff_quantiles": {q: float(np.quantile(px, float(q))) for q in ("0.5", "0.9", "0.99", "0.999", "0.9999")},
+                            "frac_pixels_above_1e-4": float((px > 1e-4).mean()), "frac_pixels_above_1e-3": float((px > 1e-3).mean()),
+                            "frac_pixels_above_1e-2": float((px > 1e-2).mean()), "psnr_reference_renderer": float(np.mean(psnr_r)),
                             "psnr_this_renderer": float(np.mean(psnr_o)), "delta_db": float(np.mean(psnr_o) - np.mean(psnr_r)),
                             "psnr_between_renderers": -10.0 * math.log10(max(mse_ro, 1e-30))}
         except Exception as e:      # report, do not fail the arm
