@@ -138,10 +138,11 @@ def global_mask_counts(mask: Optional[torch.Tensor], n_rows: int, group=None, de
     the single-GPU loss over the concatenated batch.  Pass the result as ``global_counts`` to masked_img_loss /
     masked_depth_loss and reduce the gradients with SUM (no averaging)."""
     if mask is None:      # plain means (img2mse): every row counts
-        c = torch.tensor([float(n_rows), 0.0, float(n_rows), float(n_rows)], dtype=torch.float32, device=device or "cuda")
+        c = torch.full((4,), float(n_rows), dtype=torch.float32, device=device or "cuda")      # (fill kernels only: CUDA-graph capturable)
+        c[1] = 0.0
     else:
         m = mask.reshape(-1).float()
-        c = torch.stack([(m == 1).sum().float(), (m == 0).sum().float(), m.sum(), torch.tensor(float(n_rows), device=m.device)])
+        c = torch.stack([(m == 1).sum().float(), (m == 0).sum().float(), m.sum(), torch.full((), float(n_rows), dtype=torch.float32, device=m.device)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
     return c

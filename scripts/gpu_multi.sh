@@ -1,14 +1,15 @@
 #!/bin/bash
 # Multi-GPU check (run under `gpurun --gpus N`): 2-rank NCCL gradient-equality test, then bench.py at the given rank counts.
-#   bash scripts/gpu_multi.sh TAG "2" | "2 4 8"
+#   bash scripts/gpu_multi.sh TAG "2" | "2:weak,strong 4:weak 8:weak,strong"
 TAG=${1:-r2m}; NS=${2:-2}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L | head -8
 timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -s > $OUT/pytest_multi_$TAG.log 2>&1; echo "pytest multi rc=$?"; tail -4 $OUT/pytest_multi_$TAG.log
 PORT=29511
-for N in $NS; do
-  for SC in weak strong; do
+for ITEM in $NS; do
+  N=${ITEM%%:*}; MODES=${ITEM#*:}; if [ "$MODES" = "$ITEM" ]; then MODES="weak,strong"; fi
+  for SC in ${MODES//,/ }; do
     PORT=$((PORT+1))
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 20 --warmup 3 --scaling $SC > $OUT/bench_${TAG}_${N}gpu_$SC.json 2> $OUT/bench_${TAG}_${N}gpu_$SC.err; echo "bench N=$N $SC rc=$?"
     python - <<PY
