@@ -50,7 +50,8 @@ constexpr size_t kSlotE = 0, kSlotH0 = 32768, kSlotF = kSlotH0 + 8 * 131072, kSl
 struct cnerf_weights {
     uint8_t* stream3 = nullptr;     // forward stream (mlp_fwd3.cu): [256 x 16] blocks, hi 8 KB | lo 8 KB, in consumption order
     uint8_t* stream_bwd3 = nullptr; // data-gradient chain stream (mlp_bwd_tc.cu): [256 x 16] transposed blocks
-    uint8_t* stream4 = nullptr;     // forward stream of the CTA-pair kernel (mlp_fwd4.cu): per block two 8 KB halves
+    uint8_t* stream4 = nullptr;     // experiments build: forward stream of the 64-row CTA-pair kernel (experiments/mlp_fwd4.cu)
+    uint8_t* stream6 = nullptr;     // fp16 forward stream of the M = 256 CTA-pair kernel (mlp_fwd6.cu): per unit two 4 KB halves (one per CTA)
     float* misc = nullptr;          // biases + alpha/rgb heads (fp32)
     int device = -1;
     bool packed = false;
