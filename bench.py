@@ -335,7 +335,10 @@ def roofline_of(top, kernels, kern_ms, tf_peak, hbm_peak, peak_src, step_tf, n_r
     """Roofline entry of the dominant traced kernel.  The weight-gradient stage streams its operand records from HBM (reported
     against the HBM roofline, tensor fraction beside it); the forward and the chain are tensor-pipe kernels."""
     k = kernels[top]
-    common = {"kernel": k["kernel"], "traffic": ncu_traffic(top, precision_tag), "peak_source": peak_src, "kernel_ms_per_step": kern_ms[top],
+    common = {"kernel": k["kernel"], "traffic": ncu_traffic(top, precision_tag),
+              "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the call's two launches of a step (fine + coarse network), "
+                              "like `achieved`, which is per step of the same two launches (profiles/ncu_traffic.json)",
+              "peak_source": peak_src, "kernel_ms_per_step": kern_ms[top],
               "mlp_step_tflops": step_tf, "mlp_step_tensor_frac": step_tf / tf_peak, "tensor_frac": k["frac"], "mma_per_mac": k["mma_per_mac"]}
     if top == "cnerf_mlp_bwd_weights":
         return {**common, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["hbm_frac"],
@@ -388,6 +391,24 @@ def image_render_record(cn, h, dev, rank, world, dist):
             "ms_per_image": float(ms), "rays_per_s": H * W / (float(ms) * 1e-3), "scaling": "strong"}
 
 
+def finish_multi_gpu(harnesses):
+    """End of a multi-rank run.  The captured CUDA graphs hold NCCL kernels: NCCL's communicator teardown waits until every graph
+    that references the communicator has died (measured: `destroy_process_group()` after a graphed N = 2 run never returned and the
+    launcher had to be killed), and interpreter exit destroys objects in no particular order.  So: drop the graphs explicitly,
+    drain the device, flush the streams -- and leave with os._exit, skipping destructors altogether.  Every rank has passed its last
+    collective when it gets here."""
+    import gc
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(20.0, lambda: os._exit(0)).start()      # whatever happens below, the process is gone 20 s from now
+    for h in harnesses:
+        if h is not None:
+            h.graph, h.graph_out = None, None
+    gc.collect()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
 def run_b200(args):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -427,7 +448,7 @@ def run_b200(args):
     ms_step, ms_eager, launches, kern_ms, kern_calls, ms_e2e = time_harness(h, args, dist, world)
     clk = clocks.stop() if rank == 0 else None
 
-    render_rec = None
+    render_rec, hr = None, None
     if train and not args.no_render_record:      # render-only throughput, driver-visible in the same line
         hr = Harness(args, "render", rays_per_gpu, dev, rank, world, nets=(h.coarse, h.fine))
         hr.try_capture()
@@ -446,9 +467,7 @@ def run_b200(args):
                                        "mma_per_mac": fwd_t, "note": "1.2445 TFLOP of MLP work per 4096-ray batch over the whole render step"},
                           "kernels": kernel_table(r_kern, r_calls, rays_per_gpu, terms, tf_peak, hbm_peak), "image": img}
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        finish_multi_gpu([h, hr])
 
     tf_peak, hbm_peak, peak_src = peaks()
     kernels = kernel_table(kern_ms, kern_calls, rays_per_gpu, terms, tf_peak, hbm_peak)
@@ -490,7 +509,7 @@ def run_b200(args):
     }
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        finish_multi_gpu([h, hr])
 
 
 # ----------------------------------------------------------------------------------------------
