@@ -17,9 +17,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libcnerf.so")
-SOURCES = ["api.cu", "sampling.cu", "composite.cu", "crossview.cu", "linear_simt.cu", "mlp_tc.cu", "mlp_bwd_tc.cu", "mlp_fwd3.cu", "mlp_fwd5.cu", "mlp_fwd6.cu"]
+SOURCES = ["api.cu", "sampling.cu", "composite.cu", "crossview.cu", "linear_simt.cu", "mlp_tc.cu", "mlp_bwd_tc.cu", "mlp_fwd3.cu", "mlp_fwd5.cu"]
 # opt-in experiments (a measured negative result): linked only by `--experiments` / CNERF_BUILD_EXPERIMENTS=1
-EXPERIMENT_SOURCES = ["experiments/mlp_fwd4.cu", "experiments/pair_selftest.cu"]
+EXPERIMENT_SOURCES = ["experiments/mlp_fwd4.cu", "experiments/pair_selftest.cu", "experiments/mlp_fwd6.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

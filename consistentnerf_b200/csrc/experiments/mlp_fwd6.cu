@@ -15,7 +15,11 @@
 //   TMEM      per CTA: one 256-column accumulator per slot (lane = local row)
 //   sync      full[st] (local bulk copy landed), pfull[st] (leader: the peer's half landed; forwarded by the peer's warp 17),
 //             empty[st] / d_full[slot] (multicast commits), a_ready[slot] (leader: 32 warp arrivals, 16 from each CTA)
-// Inference only for now; training runs mlp_fwd5.cu.
+// Inference only; training runs mlp_fwd5.cu.
+//
+// STATUS: written at the end of round 2, compiles for sm_100a (SASS: UTCHMMA.2CTA), but NOT RUN ON A GPU -- the round's GPU budget was
+// spent before it could be tested (scripts/test_pair.py is the parity + timing check to run first).  It is therefore built only with
+// `python -m consistentnerf_b200.build --experiments` and selected only with CNERF_FWD_PAIR=1; nothing in the product uses it.
 #include "mlp_blocks.cuh"
 
 namespace cnerf {

@@ -256,18 +256,23 @@ int launch_fused3(const uint8_t* stream3, const float* misc, const float* pts, c
                   int n_samples, int n_rays, float* raw, uint8_t* acts, int record_lo, int terms, cudaStream_t st);
 int launch_fused5(const uint8_t* stream3, const float* misc, const float* pts, const float* viewdirs, int n_points,         // mlp_fwd5.cu
                   int n_samples, int n_rays, float* raw, uint8_t* acts, cudaStream_t st);
-int pack_stream6(const RawParams& p, uint8_t* stream6, cudaStream_t st);                                                     // mlp_fwd6.cu
+#ifdef CNERF_EXPERIMENTS
+int pack_stream6(const RawParams& p, uint8_t* stream6, cudaStream_t st);                                                     // experiments/mlp_fwd6.cu
 size_t stream6_bytes();
 int launch_fused6(const uint8_t* stream6, const float* misc, const float* pts, const float* viewdirs, int n_points,
                   int n_samples, int n_rays, float* raw, cudaStream_t st);
+#endif
 }
 
-// fp16 inference forward: CNERF_FWD_PAIR=1 selects the CTA-pair kernel (mlp_fwd6.cu), 0 the single-CTA two-tile kernel (mlp_fwd5.cu)
+#ifdef CNERF_EXPERIMENTS
+// experiments build, fp16 inference forward: CNERF_FWD_PAIR=1 selects the M = 256 CTA-pair kernel (experiments/mlp_fwd6.cu) instead of
+// the single-CTA two-tile kernel (mlp_fwd5.cu)
 static bool fwd_pair() {
     static int v = -1;
     if (v < 0) { const char* ev = getenv("CNERF_FWD_PAIR"); v = (ev && ev[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+#endif
 
 // The product runs the single-CTA N=256 kernel (mlp_fwd3.cu).  A build with CNERF_EXPERIMENTS (python -m
 // consistentnerf_b200.build --experiments) also links the CTA-pair ping-pong experiment (experiments/mlp_fwd4.cu, inference
@@ -289,7 +294,9 @@ extern "C" int cnerf_weights_create(cnerf_weights** out) {
 #ifdef CNERF_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&w->stream4, stream4_bytes());
 #endif
+#ifdef CNERF_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&w->stream6, stream6_bytes());
+#endif
     if (e == cudaSuccess) e = cudaMalloc(&w->misc, kMiscFloats * sizeof(float));
     if (e != cudaSuccess) { cudaFree(w->stream3); cudaFree(w->stream_bwd3); cudaFree(w->stream4); cudaFree(w->stream6); delete w; return check_cuda(e, "cudaMalloc(weights)"); }
     *out = w;
@@ -326,7 +333,9 @@ extern "C" int cnerf_weights_refresh(cnerf_weights* w, const float* const* pts_w
 #ifdef CNERF_EXPERIMENTS
     if (rc == CNERF_OK && fwd_impl() == 4) rc = pack_stream4(p, w->stream4, as_stream(stream));
 #endif
+#ifdef CNERF_EXPERIMENTS
     if (rc == CNERF_OK && fwd_pair()) rc = pack_stream6(p, w->stream6, as_stream(stream));
+#endif
     if (rc == CNERF_OK) rc = pack_bwd_stream3(p, w->stream_bwd3, as_stream(stream));
     if (rc != CNERF_OK) return rc;
     w->packed = true;
@@ -349,8 +358,10 @@ static int launch_mlp(const cnerf_weights* w, const float* pts, const float* vie
     if (fwd_impl() == 4 && !acts && terms == 7)      // the CTA-pair experiment is inference only; training runs the single-CTA kernel
         return launch_fused4(w->stream4, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, as_stream(stream));
 #endif
+#ifdef CNERF_EXPERIMENTS
     if (fwd_terms == 1 && terms == 7 && !acts && fwd_pair())
         return launch_fused6(w->stream6, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, as_stream(stream));
+#endif
     if (fwd_terms == 1 && terms == 7)
         return launch_fused5(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, as_stream(stream));
     return launch_fused3(w->stream3, w->misc, pts, viewdirs, n_points, n_samples, n_rays, raw, (uint8_t*)acts, record_lo, terms,
