@@ -46,3 +46,29 @@ def test_b200_arm_needs_a_gpu():
         return
     res = _run("--steps", "1")
     assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
+
+
+def test_bench_line_helpers_on_synthetic_numbers():
+    """The pure bookkeeping of the B200 arm (kernel table, roofline entry, committed ncu traffic) runs on the CPU with made-up times:
+    catches key / unit mistakes that would otherwise only show on the GPU box."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tf_peak, hbm_peak, src = bench.peaks()
+    assert tf_peak > 100 and hbm_peak > 1000
+    kern_ms = {"cnerf_mlp_fwd_train": 2.05, "cnerf_mlp_bwd_data": 1.55, "cnerf_mlp_bwd_weights": 2.61}
+    calls = {k: 2.0 for k in kern_ms}
+    for terms, tag in (({"fwd": 1, "fwd_train": 1, "chain": 1, "dw": 1}, "fwd_fp16+grad_fp16"), ({"fwd": 3, "fwd_train": 3, "chain": 3, "dw": 3}, "fwd_split+grad_split")):
+        table = bench.kernel_table(kern_ms, calls, bench.N_RAYS, terms, tf_peak, hbm_peak)
+        assert set(table) == set(kern_ms)
+        dw = table["cnerf_mlp_bwd_weights"]
+        assert dw["bytes_per_point"] == bench.DW_COLUMNS_PER_POINT * (2 if terms["dw"] == 1 else 4) and 0 < dw["hbm_frac"] < 2
+        top = max(kern_ms, key=kern_ms.get)
+        roof = bench.roofline_of(top, table, kern_ms, tf_peak, hbm_peak, src, 550.0, bench.N_RAYS, tag)
+        assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+        assert roof["traffic"] is None or roof["traffic"] > 1e9
+        roof2 = bench.roofline_of("cnerf_mlp_fwd_train", table, kern_ms, tf_peak, hbm_peak, src, 550.0, bench.N_RAYS, tag)
+        assert roof2["bound"] == "tensor" and roof2["mma_per_mac"] == terms["fwd_train"] and 0 < roof2["frac"] < 1
+    assert bench.ncu_traffic("cnerf_mlp_bwd_weights", "fwd_fp16+grad_fp16") > 1e10       # committed capture: 11.4 GB per step
+    assert bench.ncu_traffic("cnerf_mlp_bwd_weights", "no such mode") is None
+    o, d, tgt, prior, mask = bench.make_batch(64, 3)
+    assert o.shape == (64, 3) and mask.shape == (64, 1) and float(d.norm(dim=-1).sub(1).abs().max()) < 1e-6
