@@ -1,4 +1,4 @@
-// Weight-block program of the N=256 forward kernels (mlp_fwd3.cu single CTA, mlp_fwd4.cu CTA pair) and the epilogue /
+// Weight-block program of the N=256 forward kernels (mlp_fwd3.cu three-term, mlp_fwd5.cu fp16 two-tile, experiments/: CTA pairs) and the epilogue /
 // encoding helpers they share.
 #pragma once
 #include "mlp_layout.cuh"

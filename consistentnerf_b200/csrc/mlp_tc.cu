@@ -1,4 +1,4 @@
-// Weight handle, the C-ABI entry points of the fused MLP forward (the kernels live in mlp_fwd3.cu / mlp_fwd4.cu), and the unit
+// Weight handle, the C-ABI entry points of the fused MLP forward (the kernels live in mlp_fwd3.cu / mlp_fwd5.cu), and the unit
 // self-tests / issue-rate microbenchmark of the tcgen05 building blocks (sm_100a).
 //
 // Precision ("fp16x3"): every fp32 operand x is carried as hi = fp16(x), lo = fp16(x - hi) and a
@@ -274,7 +274,7 @@ static bool fwd_pair() {
 }
 #endif
 
-// The product runs the single-CTA N=256 kernel (mlp_fwd3.cu).  A build with CNERF_EXPERIMENTS (python -m
+// The product runs the single-CTA kernels (mlp_fwd3.cu three-term, mlp_fwd5.cu fp16).  A build with CNERF_EXPERIMENTS (python -m
 // consistentnerf_b200.build --experiments) also links the CTA-pair ping-pong experiment (experiments/mlp_fwd4.cu, inference
 // only, correct but 2.4x slower), selected once per process with CNERF_MLP_IMPL=4.
 #ifdef CNERF_EXPERIMENTS

@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the fp16 hi/lo operand helpers shared by the
-// tensor-core kernels (mlp_fwd3.cu / mlp_fwd4.cu forward, mlp_bwd_tc.cu backward).  sm_100a only.
+// tensor-core kernels (mlp_fwd3.cu / mlp_fwd5.cu forward, mlp_bwd_tc.cu backward, experiments/).  sm_100a only.
 #pragma once
 #include "common.cuh"
 
