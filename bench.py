@@ -401,8 +401,10 @@ def finish_multi_gpu(harnesses=None):
     sys.stdout.flush()
     sys.stderr.flush()
     threading.Timer(20.0, lambda: os._exit(0)).start()
-    torch.cuda.synchronize()          # (releases the GIL while waiting: the timer can always fire)
-    os._exit(0)
+    try:
+        torch.cuda.synchronize()      # (releases the GIL while waiting: the timer can always fire)
+    finally:
+        os._exit(0)
 
 
 def run_b200(args):

@@ -72,3 +72,32 @@ def test_bench_line_helpers_on_synthetic_numbers():
     assert bench.ncu_traffic("cnerf_mlp_bwd_weights", "no such mode") is None
     o, d, tgt, prior, mask = bench.make_batch(64, 3)
     assert o.shape == (64, 3) and mask.shape == (64, 1) and float(d.norm(dim=-1).sub(1).abs().max()) < 1e-6
+
+
+_EXIT_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import bench
+dist.init_process_group("gloo")
+t = torch.ones(3) * (dist.get_rank() + 1)
+dist.all_reduce(t)
+if dist.get_rank() == 0:
+    print("SUM", t.tolist())
+bench.finish_multi_gpu()          # no teardown: flush, os._exit(0)
+print("NOT REACHED")
+"""
+
+
+def test_multi_rank_exit_tears_nothing_down(tmp_path):
+    """bench.finish_multi_gpu(): both ranks of a torchrun launch leave with exit code 0 right after their last collective, the
+    line printed before is not lost, and nothing after the call runs (CPU / gloo stand-in for the NCCL case)."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "exit_check.py"
+    script.write_text(_EXIT_SCRIPT % ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "SUM [3.0, 3.0, 3.0]" in res.stdout and "NOT REACHED" not in res.stdout
