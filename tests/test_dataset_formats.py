@@ -192,3 +192,53 @@ def test_metrics_file_with_cuda_tensor_repr(tmp_path):
     assert m == {"PSNR": 23.5, "SSIM": 0.8125, "LPIPS": 0.1234}
     (tmp_path / "m2.txt").write_text("PSNR: 2.5e+01\nSSIM: -1.5E-3\nLPIPS: tensor(1.2500e-04, device='cuda:0')")
     assert formats.read_metrics(str(tmp_path / "m2.txt")) == {"PSNR": 25.0, "SSIM": -0.0015, "LPIPS": 0.000125}
+
+
+@needs_ref
+def test_llff_scene_through_the_reference_full_loader(tmp_path):
+    """load_llff_data end to end (rescale by bd_factor, recenter, spiral render path, hold-out choice; NP/load_llff.py:288-356) on a
+    forward-facing scene written by formats.write_llff_scene: 20 cameras on a small grid looking down -z, LLFF axis order."""
+    from consistentnerf_b200 import formats
+    ll = _import_ref("load_llff")
+    rng = np.random.RandomState(5)
+    n, h, w, factor, focal = 20, 6, 8, 8, 50.0
+    imgs = (rng.rand(n, h, w, 3) * 255).astype(np.uint8)
+    pb = np.zeros((n, 17))
+    for i in range(n):
+        pos = np.array([0.6 * (i % 5) / 4 - 0.3, 0.4 * (i // 5) / 3 - 0.2, 0.05 * rng.randn()])
+        # camera axes in the world: right = +x, up = +y, back = +z (looking down -z); LLFF stores [down, right, back]
+        R = np.stack([np.array([0, -1.0, 0]), np.array([1.0, 0, 0]), np.array([0, 0, 1.0])], 1)
+        p = np.concatenate([R, pos[:, None], np.array([[h * factor], [w * factor], [focal * factor]])], 1)
+        pb[i, :15], pb[i, 15:] = p.reshape(-1), [2.0 + 0.1 * rng.rand(), 8.0 + rng.rand()]
+    formats.write_llff_scene(str(tmp_path / "fern"), imgs, pb, factor=factor)
+    images, poses, bds, render_poses, i_test, mono = ll.load_llff_data(str(tmp_path / "fern"), factor, recenter=True, bd_factor=0.75, spherify=False)
+    assert images.shape == (n, h, w, 3) and poses.shape == (n, 3, 5) and render_poses.shape == (60, 3, 4) and mono.shape[0] == n
+    assert np.array_equal((images * 255 + 0.5).astype(np.uint8), imgs)
+    sc = 1.0 / (pb[:, 15].min() * 0.75)
+    np.testing.assert_allclose(bds, pb[:, 15:] * sc, rtol=1e-6)
+    np.testing.assert_allclose(poses[:, :, 4], np.tile([h, w, focal], (n, 1)), rtol=1e-6)          # hwf: loaded shape, focal / factor
+    # after the loader's axis swap the rotation is [right, up, back] = identity here, and recentring keeps it so
+    np.testing.assert_allclose(poses[:, :3, :3], np.tile(np.eye(3), (n, 1, 1)), atol=1e-5)
+    np.testing.assert_allclose(poses[:, :3, 3].mean(0), 0.0, atol=1e-5)                              # recentred around the mean camera
+    assert 0 <= int(i_test) < n
+    mine = formats.load_llff_scene(str(tmp_path / "fern"), factor=factor)
+    assert np.array_equal(np.moveaxis(mine[2], -1, 0).astype(np.float32), images)
+
+
+@needs_ref
+def test_config1_reference_script_trains_on_the_cpu(tmp_path):
+    """BASELINE config 1: the unmodified run_nerf.py -- Blender loader, 64 x 64, N_samples = 32, coarse only, no view directions -- runs its
+    own train() on the CPU on a scene written by this package (formats + shims + twin harness; the product itself has no CPU path).
+    10 iterations: plumbing, not quality."""
+    sys.path.insert(0, ROOT)
+    from oracle import twin
+    if not os.path.isdir(twin.REF):
+        pytest.skip("oracle/_ref not populated")
+    root = str(tmp_path / "cfg1")
+    twin.make_scene("blender", root, res=64)
+    res = twin.run_arm_subprocess("ref", "blender", root, iters=10, eval_views=1, extra_args=twin.CONFIG1, device="cpu", timeout=900)
+    assert "error" not in res, res
+    assert res["device"] == "cpu" and res["patched"] == [] and res["checkpoints"] == []      # (run_nerf.py cannot checkpoint without a fine net)
+    assert 5.0 < res["psnr"] < 60.0 and res["train_ms_per_iter"] > 0
+    log = open(os.path.join(root, "log_blender_ref.txt")).read()
+    assert "Loaded blender (5, 64, 64, 4)" in log and "TRAIN views are" in log            # 3 train + 1 val + 1 test views
