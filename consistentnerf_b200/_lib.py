@@ -54,6 +54,8 @@ SIGNATURES = {
     "cnerf_hard_mask_pair": (_I, [_P, _P, _P, _I, POINTER(c_float), POINTER(c_float), _P, _I, _I, _F, _I, _I, _P, _P]),
     "cnerf_masked_mse_fwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
     "cnerf_masked_mse_bwd": (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "cnerf_soft_mse_fwd": (_I, [_P, _P, c_int64, _F, _I, _F, _P, _P, _P, _P]),
+    "cnerf_soft_mse_bwd": (_I, [_P, _P, c_int64, _F, _I, _P, _P, _P, _P]),
 }
 
 # include/cnerf_debug.h: self-tests, microbenchmarks, profiling hooks -- not part of the drop-in boundary
@@ -107,7 +109,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful call (1 unless listed): the bench's gpu_launches claim is counted here
-LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 3, "cnerf_mlp_bwd": 7, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 3, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
+LAUNCHES_PER_CALL = {"cnerf_weights_refresh": 3, "cnerf_mlp_bwd": 7, "cnerf_mlp_bwd_data": 2, "cnerf_mlp_bwd_weights": 3, "cnerf_mlp_bwd_heads": 2, "cnerf_masked_mse_fwd": 2, "cnerf_soft_mse_fwd": 2, "cnerf_linear_bwd_weight": 4}
 launch_count = 0
 # name -> list of (start, end) CUDA event pairs; filled only for the names put into the dict by a profiler
 event_trace = {}

@@ -59,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False, experiments: bool 
     os.makedirs(OBJ, exist_ok=True)
     sources = SOURCES + (EXPERIMENT_SOURCES if experiments else [])
     flags = NVCC_FLAGS + (["-DCNERF_EXPERIMENTS"] if experiments else [])
-    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(CSRC, h) for h in ("common.cuh", "umma.cuh", "mlp_layout.cuh", "mlp_blocks.cuh")] + [
+    deps = [os.path.join(CSRC, s) for s in sources] + [os.path.join(CSRC, h) for h in ("common.cuh", "umma.cuh", "mlp_layout.cuh", "mlp_blocks.cuh", "soft_weight.h")] + [
         os.path.join(PKG, "..", "include", "cnerf.h"), os.path.join(PKG, "..", "include", "cnerf_debug.h")]
     stamp = os.path.join(OBJ, "stamp")
     digest = _digest(deps, flags)

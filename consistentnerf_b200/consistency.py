@@ -123,3 +123,25 @@ def masked_depth_loss(depth_pred, depth_prior, mask, far: float, hardmask_coef: 
     loss, stats = ops.MaskedMSEFn.apply(depth_pred.reshape(-1, 1), depth_prior.reshape(-1, 1), mask, float(far),
                                         float(hardmask_coef), n_ref, bool(include_unmasked), global_counts)
     return (loss, stats) if return_stats else loss
+
+
+def img2mse_softmask(x, y, temp):
+    """sum(exp((x - y)^2 / temp) (x - y)^2) / sum(exp((x - y).detach()^2 / temp))   (NP/run_nerf_view.py:50); ``temp`` a float or the
+    one-element device tensor softplus(network_fine.temp_rgb) (:1659), which then receives its gradient."""
+    return ops.SoftMSEFn.apply(x, y, temp, 1.0, 0)
+
+
+def img2mse_depth_softmask(x, y, temp):
+    """The depth twin of img2mse_softmask (NP/run_nerf_view.py:55; same expression, called on depth / far, :1759)."""
+    return ops.SoftMSEFn.apply(x, y, temp, 1.0, 0)
+
+
+def img2mse_softLpmask(x, y, coef):
+    """sum((|x - y|^coef + 1) (x - y)^2) / sum(|x - y|^coef + 1).detach()   (NP/run_nerf_view.py:58, --softLpmask, :1663-1664)."""
+    return ops.SoftMSEFn.apply(x, y, float(coef), 1.0, 1)
+
+
+def soft_depth_loss(depth_pred, depth_prior, far: float, param, kind: int = 1):
+    """The scripts' depth form: the loss of depth_pred / far against depth_prior / far (NP/run_nerf_view.py:1759,1761) with the
+    division done inside the kernel."""
+    return ops.SoftMSEFn.apply(depth_pred, depth_prior, param if isinstance(param, torch.Tensor) else float(param), float(far), int(kind))

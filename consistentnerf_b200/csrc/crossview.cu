@@ -5,6 +5,7 @@
 // round-to-nearest intrinsics (no FMA contraction) so that the rounded pixel coordinates are
 // reproducible bit for bit against the oracle (oracle/nerf_oracle.py: project_points).
 #include "common.cuh"
+#include "soft_weight.h"
 
 namespace cnerf {
 
@@ -192,6 +193,57 @@ __global__ void masked_mse_bwd_kernel(const float* __restrict__ pred, const floa
     d_pred[idx] = g_loss[0] * wgt * 2.f * d / divisor;
 }
 
+// ------------------------------------------------------------------------------------
+// K7b soft-weighted MSE (img2mse_softmask / img2mse_depth_softmask / img2mse_softLpmask, NP/run_nerf_view.py:50-58);
+// element arithmetic in soft_weight.h.  Same deterministic two-stage reduction as K7.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads)
+soft_mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t total, float divisor,
+                        int kind, float param_host, const float* __restrict__ param_dev, double* __restrict__ part) {
+    const float param = param_dev ? param_dev[0] : param_host;
+    double num = 0.0, den = 0.0, s4 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float d = cnerf_soft_residual(pred[i], target[i], divisor);
+        double w = (double)cnerf_soft_weight(d, kind, param), e = (double)(d * d);
+        num += w * e; den += w; s4 += w * e * e;
+    }
+    __shared__ double sh[kLossThreads / 32][3];
+    double v[3] = {warp_sum(num), warp_sum(den), warp_sum(s4)};
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) sh[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) t += sh[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+
+__global__ void soft_mse_final_kernel(const double* __restrict__ part, int nblocks, int kind, float param_host,
+                                      const float* __restrict__ param_dev, float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    const float param = param_dev ? param_dev[0] : param_host;
+    double v[3] = {0, 0, 0};
+    for (int b = 0; b < nblocks; ++b)
+        for (int k = 0; k < 3; ++k) v[k] += part[(size_t)b * 3 + k];
+    double loss, dparam;
+    cnerf_soft_finish(v[0], v[1], v[2], kind, (double)param, &loss, &dparam);
+    out[0] = (float)loss;
+    out[1] = (float)v[0];
+    out[2] = (float)v[1];
+    out[3] = (float)dparam;
+    out[4] = param;
+}
+
+__global__ void soft_mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t total,
+                                    float divisor, int kind, const float* __restrict__ out,
+                                    const float* __restrict__ g_loss, float* __restrict__ d_pred) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float d = cnerf_soft_residual(pred[i], target[i], divisor);
+    d_pred[i] = g_loss[0] * cnerf_soft_dnum(d, kind, out[4]) / out[2] / divisor;
+}
+
 static Cam make_cam(const float* w2c, const float* K) {
     Cam c;
     for (int r = 0; r < 3; ++r) {
@@ -259,5 +311,33 @@ extern "C" int cnerf_masked_mse_bwd(const float* pred, const float* target, cons
     masked_mse_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
         pred, target, mask, n, C, divisor, coef, n_ref, use_unmasked, out, g_loss, d_pred);
     CNERF_LAUNCH_CHECK("masked_mse_bwd_kernel");
+    return CNERF_OK;
+}
+
+extern "C" int cnerf_soft_mse_fwd(const float* pred, const float* target, int64_t n_elems, float divisor, int kind,
+                                  float param, const float* param_dev, float* out, void* workspace, void* stream) {
+    CNERF_REQUIRE(((pred && target) || n_elems == 0) && out && workspace, "cnerf_soft_mse_fwd: null pointer");
+    CNERF_REQUIRE(n_elems >= 0 && (kind == 0 || kind == 1) && divisor != 0.f, "cnerf_soft_mse_fwd: bad arguments");
+    CNERF_REQUIRE(param_dev || (kind == 0 ? param > 0.f : param >= 1.f),
+                  "cnerf_soft_mse_fwd: temp must be > 0 (kind 0), the exponent >= 1 (kind 1)");
+    int64_t want = ceil_div64(n_elems, kLossThreads);
+    int blocks = want < 1 ? 1 : (want < kLossBlocks ? (int)want : kLossBlocks);
+    double* part = reinterpret_cast<double*>(workspace);
+    soft_mse_partial_kernel<<<blocks, kLossThreads, 0, as_stream(stream)>>>(pred, target, n_elems, divisor, kind, param,
+                                                                            param_dev, part);
+    CNERF_LAUNCH_CHECK("soft_mse_partial_kernel");
+    soft_mse_final_kernel<<<1, 32, 0, as_stream(stream)>>>(part, blocks, kind, param, param_dev, out);
+    CNERF_LAUNCH_CHECK("soft_mse_final_kernel");
+    return CNERF_OK;
+}
+
+extern "C" int cnerf_soft_mse_bwd(const float* pred, const float* target, int64_t n_elems, float divisor, int kind,
+                                  const float* out, const float* g_loss, float* d_pred, void* stream) {
+    CNERF_REQUIRE(((pred && target && d_pred) || n_elems == 0) && out && g_loss, "cnerf_soft_mse_bwd: null pointer");
+    CNERF_REQUIRE(n_elems >= 0 && (kind == 0 || kind == 1) && divisor != 0.f, "cnerf_soft_mse_bwd: bad arguments");
+    if (n_elems == 0) return CNERF_OK;
+    soft_mse_bwd_kernel<<<(unsigned)ceil_div64(n_elems, 256), 256, 0, as_stream(stream)>>>(pred, target, n_elems, divisor,
+                                                                                           kind, out, g_loss, d_pred);
+    CNERF_LAUNCH_CHECK("soft_mse_bwd_kernel");
     return CNERF_OK;
 }

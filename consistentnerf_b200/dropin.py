@@ -27,6 +27,7 @@ from .render import make_api        # (the package attribute `render` is the fun
 _RENDER_NAMES = ["batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays"]
 _MODEL_NAMES = ["NeRF", "Embedder", "get_embedder", "sample_pdf", "get_rays", "ndc_rays"]
 _VIEW_NAMES = ["get_rays_ref", "get_ref_rays", "get_test_label"]
+_LOSS_NAMES = ["img2mse_softmask", "img2mse_depth_softmask", "img2mse_softLpmask"]      # --softLpmask (NP/run_nerf_view.py:1663)
 
 
 def wants_depth(module) -> bool:
@@ -49,7 +50,7 @@ def patch(module, with_depth=None):
         if hasattr(module, name):
             setattr(module, name, getattr(nerf, name))
             done.append(name)
-    for name in _VIEW_NAMES:
+    for name in _VIEW_NAMES + _LOSS_NAMES:
         if hasattr(module, name):
             setattr(module, name, getattr(consistency, name))
             done.append(name)

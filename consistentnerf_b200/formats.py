@@ -307,3 +307,23 @@ def load_llff_scene(basedir: str, factor: int = 8):
     poses[:2, 4, :] = np.array(imgs.shape[:2]).reshape([2, 1])
     poses[2, 4, :] = poses[2, 4, :] * 1.0 / factor
     return poses, bds, imgs
+
+
+def softmask_path(root: str, dataset_type: str, scene: str, index: int, top_k: int = 30) -> str:
+    """Where train(--softmask) looks for the mask of training view ``index`` (NP/run_nerf_view.py:1049-1050; relative to the working
+    directory there, to ``root`` here)."""
+    return os.path.join(root, "Softmask", dataset_type, scene, "iter_500", f"softmask_{index:04d}_{top_k}per.png")
+
+
+def write_softmask(root: str, dataset_type: str, scene: str, index: int, mask: np.ndarray, top_k: int = 30) -> str:
+    """An 8-bit single-channel PNG; the script keeps ``value > 0`` as the mask (NP/run_nerf_view.py:1051,1054)."""
+    path = softmask_path(root, dataset_type, scene, index, top_k)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    m = np.asarray(mask)
+    _write_png(path, (m.astype(np.float32) * 255.0 + 0.5).astype(np.uint8) if m.dtype != np.uint8 else m)
+    return path
+
+
+def read_softmask(root: str, dataset_type: str, scene: str, index: int, top_k: int = 30) -> np.ndarray:
+    """The boolean [H, W] mask the script builds from the file: (png / 255) > 0."""
+    return (_read_png(softmask_path(root, dataset_type, scene, index, top_k)).astype(np.float32) / 255.0) > 0

@@ -690,6 +690,44 @@ class MaskedMSEFn(torch.autograd.Function):
         return d.reshape(shape), None, None, None, None, None, None, None
 
 
+class SoftMSEFn(torch.autograd.Function):
+    """K7b: soft-weighted MSE, kind 0 = img2mse_softmask / img2mse_depth_softmask(x, y, temp), kind 1 = img2mse_softLpmask(x, y,
+    coef) (NP/run_nerf_view.py:50-58).  ``param`` is a python float or a one-element tensor (temp = softplus(network.temp_rgb) in the
+    reference, :1659 -- read on the device, no sync); a tensor ``param`` of kind 0 gets its gradient."""
+
+    @staticmethod
+    def forward(ctx, pred, target, param, divisor: float, kind: int):
+        _need_cuda(pred, "soft_mse")
+        if pred.shape != target.shape:
+            raise ValueError(f"soft_mse: pred {tuple(pred.shape)} and target {tuple(target.shape)} differ")
+        p = _f32c(pred.detach()).reshape(-1)
+        t = _f32c(target.detach()).reshape(-1)
+        on_device = isinstance(param, torch.Tensor)
+        pd = _f32c(param.detach()).reshape(-1) if on_device else None
+        if on_device and (pd.numel() != 1 or not pd.is_cuda):
+            raise ValueError("soft_mse: the parameter tensor must be one CUDA element")
+        out = torch.empty(5, device=p.device, dtype=_F32)
+        ws = _workspace(p.device, 8192)
+        call("cnerf_soft_mse_fwd", ptr(p), ptr(t), p.numel(), float(divisor), int(kind), 1.0 if on_device else float(param),
+             ptr(pd), ptr(out), ptr(ws), stream())
+        ctx.save_for_backward(p, t, out)
+        ctx.cfg = (float(divisor), int(kind), pred.shape, param.shape if on_device else None)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        p, t, out = ctx.saved_tensors
+        divisor, kind, shape, param_shape = ctx.cfg
+        g = _f32c(g_loss).reshape(1)
+        d = None
+        if ctx.needs_input_grad[0]:
+            d = torch.empty_like(p)
+            call("cnerf_soft_mse_bwd", ptr(p), ptr(t), p.numel(), divisor, kind, ptr(out), ptr(g), ptr(d), stream())
+            d = d.reshape(shape)
+        d_param = (g * out[3]).reshape(param_shape) if (param_shape is not None and ctx.needs_input_grad[2]) else None
+        return d, None, d_param, None, None
+
+
 def umma_selftest(a: torch.Tensor, b: torch.Tensor, a_in_tmem: bool = False) -> torch.Tensor:
     """d = a b^T through the tcgen05 building blocks (a [128,k], b [n,k]); A from SMEM or from tensor memory.
     a [256,k]: the CTA-pair (cta_group::2) variant."""

@@ -244,6 +244,19 @@ int cnerf_masked_mse_bwd(const float* pred, const float* target, const float* ma
                          float divisor, float coef, float n_ref, int use_unmasked, const float* out,
                          const float* g_loss, float* d_pred, void* stream);
 
+/* K7b soft-weighted MSE over n_elems values -- replaces img2mse_softmask / img2mse_depth_softmask (kind 0, param = temp)
+ * NP/run_nerf_view.py:50,55 and img2mse_softLpmask (kind 1, param = coef) NP/run_nerf_view.py:58:
+ *   d = pred / divisor - target / divisor,   w = exp(d^2 / temp)  |  |d|^coef + 1,   loss = sum(w d^2) / sum(w)
+ * with sum(w) a constant for d (the reference detaches it) but, for kind 0, a function of temp.  The parameter is read from
+ * param_dev[0] when that device pointer is non-NULL (temp = softplus(network_fine.temp_rgb) is a device scalar in the
+ * reference, :1659) and from `param` otherwise.  out[5] = {loss, sum(w d^2), sum(w), d loss / d param (0 for kind 1), param}.
+ * workspace: 8192 bytes of scratch.  Deterministic reduction order.  n_elems == 0 gives NaN like the reference (0 / 0). */
+int cnerf_soft_mse_fwd(const float* pred, const float* target, int64_t n_elems, float divisor, int kind, float param,
+                       const float* param_dev, float* out, void* workspace, void* stream);
+/* d_pred [n_elems] = g_loss[0] * d out[0] / d pred, using sum(w) and the parameter stored in `out` by the forward. */
+int cnerf_soft_mse_bwd(const float* pred, const float* target, int64_t n_elems, float divisor, int kind, const float* out,
+                       const float* g_loss, float* d_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

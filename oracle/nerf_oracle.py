@@ -388,6 +388,17 @@ def masked_mse(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, coe
     return loss
 
 
+def soft_mse(x: torch.Tensor, y: torch.Tensor, param, kind: int) -> torch.Tensor:
+    """The soft-weighted losses, differentiable like the reference's lambdas (only (x - y) of the denominator is detached):
+    kind 0  img2mse_softmask / img2mse_depth_softmask(x, y, temp)   NP/run_nerf_view.py:50,55
+    kind 1  img2mse_softLpmask(x, y, coef)                          NP/run_nerf_view.py:58."""
+    d = x - y
+    if kind == 0:
+        return torch.sum(torch.exp(d ** 2 / param) * d ** 2) / torch.sum(torch.exp(d.detach() ** 2 / param))
+    w = d.abs() ** param + 1
+    return torch.sum(w * d ** 2) / torch.sum(w).detach()
+
+
 def mse_to_psnr(x: torch.Tensor) -> torch.Tensor:
     """NP/run_nerf_helpers.py:10."""
     return -10.0 * torch.log(x) / math.log(10.0)

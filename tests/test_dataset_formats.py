@@ -242,3 +242,17 @@ def test_config1_reference_script_trains_on_the_cpu(tmp_path):
     assert 5.0 < res["psnr"] < 60.0 and res["train_ms_per_iter"] > 0
     log = open(os.path.join(root, "log_blender_ref.txt")).read()
     assert "Loaded blender (5, 64, 64, 4)" in log and "TRAIN views are" in log            # 3 train + 1 val + 1 test views
+
+
+def test_softmask_png_round_trip_through_the_imageio_shim(tmp_path):
+    """--softmask masks (NP/run_nerf_view.py:1047-1054): written here, read the way the script does (imageio.imread / 255 > 0)."""
+    from consistentnerf_b200 import formats, shims
+    shims.install()
+    import imageio
+    rng = np.random.RandomState(2)
+    mask = rng.rand(12, 16) > 0.7
+    path = formats.write_softmask(str(tmp_path), "dtu", "scan21", 3, mask, top_k=30)
+    assert path.endswith(os.path.join("Softmask", "dtu", "scan21", "iter_500", "softmask_0003_30per.png"))
+    script_side = (imageio.imread(path).astype(np.float32) / 255.0).reshape(-1) > 0
+    assert np.array_equal(script_side.reshape(12, 16), mask)
+    assert np.array_equal(formats.read_softmask(str(tmp_path), "dtu", "scan21", 3), mask)
