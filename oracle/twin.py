@@ -6,7 +6,7 @@ and once with the hot path swapped in by ``consistentnerf_b200.dropin`` -- and t
 TEST / BENCH INFRASTRUCTURE (lives under oracle/): used by tests/, bench.py's ``quality`` and ``gpu_eager`` legs and
 scripts/psnr_twin.sh; never by the product.
 
-  python oracle/twin.py make    --kind blender|dtu|llff --root DIR [--res N]      write a synthetic scene in the reference's format
+  python oracle/twin.py make    --kind blender|blender_view|dtu|llff --root DIR [--res N]      write a synthetic scene in the reference's format
   python oracle/twin.py run     --arm ref|repo --kind ... --root DIR --iters N    train() of the unmodified script + held-out PSNR
   python oracle/twin.py twin    --kind ... --root DIR --iters N                    make + both arms (subprocesses) -> one JSON line
   python oracle/twin.py eager   [--rays 4096] [--steps K]                          reference functions, GPU eager, workload A timing
@@ -39,6 +39,8 @@ SCRIPT_OF = {"blender": "run_nerf", "dtu": "run_nerf_view", "llff": "run_nerf_vi
 FULL = ["--use_viewdirs", "--N_samples", "64", "--N_importance", "128", "--N_rand", "4096"]          # configs 2-4
 CONFIG1 = ["--N_samples", "32", "--N_importance", "0", "--N_rand", "1024"]                             # config 1: coarse only, CPU plumbing
 DTU_TRAIN, DTU_VAL = [25, 21, 33], [32, 24, 23, 44]                 # dtu_train[:3] / dtu_val of NP/configs/pairs.th
+FERN_TRAIN, FERN_VAL = [17, 2, 7, 6, 11, 1], [12, 13, 5, 19]         # fern_train[:6] / fern_val of NP/configs/pairs.th
+LLFF_H, LLFF_W, LLFF_FACTOR, LLFF_VIEWS = 378, 504, 8, 20           # factor-8 fern: train() resizes the prior depths to exactly this (NP/run_nerf_view.py:836)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -189,6 +191,51 @@ def make_dtu(root: str, seed: int = 0, scan: str = "scan114", n_val_render: int 
     return {"kind": "dtu", "root": root, "config": cfg, "H": H, "W": W, "focal": focal, "near": near, "far": far, "scan": scan}
 
 
+def make_llff(root: str, seed: int = 0, scene: str = "fern") -> dict:
+    """LLFF stand-in (BASELINE config 4): 20 forward-facing cameras on a jittered grid looking at a blob cluster ~4 units down -z,
+    378 x 504 at factor 8, six training + four validation views rendered by the teacher (the others are loaded, never looked at);
+    <root>/data/nerf_llff_data/<scene> (poses_bounds.npy in LLFF axis order, images/, images_8/), prior depths
+    <root>/nerf_llff_data_depth/<scene>/*.pfm in the units train() uses them in -- z-depth in the loader's RESCALED world
+    (1 / (0.75 min bound), NP/load_llff.py:300-303; the recentring is rigid) -- and configs/pairs.th.  The config trains through
+    the NDC path (no `no_ndc`: near 0 / far 1, NP/run_nerf_view.py:876-878) with the hard masks on and the official fern recipe's
+    raw_noise_std = 1."""
+    from consistentnerf_b200 import formats
+    H, W, factor = LLFF_H, LLFF_W, LLFF_FACTOR
+    teacher = Teacher(seed + 11, extent=0.9, centre=(0.0, 0.0, -4.0))
+    focal = 407.5                                                    # fern: 3260 px at full resolution / 8
+    K = [[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]]
+    near_t, far_t = 2.0, 6.5
+    rng = np.random.RandomState(seed + 5)
+    rendered = set(FERN_TRAIN + FERN_VAL)
+    imgs, rows, priors = [], [], []
+    bd_lo, bd_hi = 2.5, 6.0
+    sc = 1.0 / (bd_lo * 0.75)                                        # what load_llff_data will multiply translations and bounds with
+    for i in range(LLFF_VIEWS):
+        eye = [0.9 * ((i % 5) / 4.0 - 0.5) + rng.uniform(-0.05, 0.05), 0.6 * ((i // 5) / 3.0 - 0.5) + rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05)]
+        c2w = look_at_gl(eye, target=(0.0, 0.0, -4.0), up=(0.0, 1.0, 0.0))
+        if i in rendered:
+            rgb, depth, acc = teacher.render(H, W, K, c2w, near_t, far_t, white_bkgd=False, n_samples=128)
+            imgs.append((255 * np.clip(rgb, 0, 1) + 0.5).astype(np.uint8))
+            prior = (depth + (1 - acc) * far_t) * sc
+            priors.append((prior + rng.normal(0.0, 0.01, size=prior.shape)).astype(np.float32))
+        else:
+            imgs.append(np.zeros((H, W, 3), np.uint8))
+            priors.append(np.full((H, W), far_t * sc, np.float32))
+        llff = np.concatenate([-c2w[:3, 1:2], c2w[:3, 0:1], c2w[:3, 2:3], c2w[:3, 3:4], np.array([[H * factor], [W * factor], [focal * factor]])], 1)
+        rows.append(np.concatenate([llff.reshape(-1), [bd_lo + (0.0 if i == 0 else rng.uniform(0, 0.3)), bd_hi + rng.uniform(0, 0.5)]]))
+    formats.write_llff_scene(os.path.join(root, "data", "nerf_llff_data", scene), np.stack(imgs), np.stack(rows), factor=factor)
+    os.makedirs(os.path.join(root, "nerf_llff_data_depth", scene), exist_ok=True)
+    for i, d in enumerate(priors):
+        formats.write_pfm(os.path.join(root, "nerf_llff_data_depth", scene, f"depth_{i:04d}.pfm"), d)
+    formats.write_pairs(os.path.join(root, "configs", "pairs.th"),
+                        {f"{scene}_train": FERN_TRAIN, f"{scene}_val": FERN_VAL, "dtu_train": list(range(16))})
+    cfg = os.path.join(root, "config_llff.txt")
+    with open(cfg, "w") as f:
+        f.write(f"expname = twin_{scene}\nbasedir = ./logs\ndatadir = ./data/nerf_llff_data/{scene}\ndataset_type = llff\n\nfactor = {factor}\nllffhold = 8\n\n"
+                "no_batching = True\nlrate_decay = 250\nraw_noise_std = 1e0\ntrain_view_num = 6\n\nhardmask = True\n")
+    return {"kind": "llff", "root": root, "config": cfg, "H": H, "W": W, "focal": focal, "near": 0.0, "far": 1.0, "scene": scene, "bd_scale": sc}
+
+
 def make_scene(kind: str, root: str, res: int = 400, seed: int = 0, n_train: int = 3) -> dict:
     os.makedirs(root, exist_ok=True)
     meta_path = os.path.join(root, f"scene_{kind}.json")
@@ -203,6 +250,8 @@ def make_scene(kind: str, root: str, res: int = 400, seed: int = 0, n_train: int
         meta["kind"] = "blender_view"
     elif kind == "dtu":
         meta = make_dtu(root, seed=seed)
+    elif kind == "llff":
+        meta = make_llff(root, seed=seed)
     else:
         raise ValueError(kind)
     meta["make_seconds"] = time.time() - t0
@@ -233,6 +282,25 @@ def _heldout(meta):
         H, W = d["images"].shape[1:3]
         K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])      # what train() builds from hwf (NP/run_nerf_view.py:961-967)
         return d["poses"], d["images"], K, float(meta["near"]), float(meta["far"])
+    if meta["kind"] == "llff":
+        # the poses the script trains in are the loader's: rescaled and recentred (NP/load_llff.py:288-356) -- take them from the reference loader
+        import contextlib
+        import io
+        import load_llff                                             # oracle/_ref (on sys.path in run_arm)
+        cwd = os.getcwd()
+        os.chdir(meta["root"])                                       # (the loader probes ./data/midas_llff_depth relative to the cwd)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                images, poses, _bds, _rp, _it, _mono = load_llff.load_llff_data(os.path.join("data", "nerf_llff_data", meta["scene"]), LLFF_FACTOR,
+                                                                                recenter=True, bd_factor=.75, spherify=False)
+        finally:
+            os.chdir(cwd)
+        focal = float(poses[0, 2, 4])
+        H, W = images.shape[1:3]
+        K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+        c2w = np.tile(np.eye(4, dtype=np.float32), (len(FERN_VAL), 1, 1))
+        c2w[:, :3, :4] = poses[FERN_VAL, :3, :4]
+        return c2w, images[FERN_VAL].astype(np.float32), K, 0.0, 1.0  # NDC: near 0, far 1 (NP/run_nerf_view.py:876-878)
     raise ValueError(meta["kind"])
 
 
@@ -253,6 +321,10 @@ def run_arm(arm: str, kind: str, root: str, iters: int, seed: int = 0, eval_view
     os.chdir(root)
     script = SCRIPT_OF[kind]
     import importlib
+    if device == "cpu":                # run_nerf_view.py asks for the current CUDA device at import (:40) even when it then runs on the host
+        torch.cuda.current_device = lambda: 0
+        torch.Tensor.cuda = lambda self, *a, **k: self              # ... and get_ref_rays calls .cuda() on its constants (:596)
+        torch.cuda.LongTensor = torch.LongTensor                    # ... and casts its pixel indices with .type(torch.cuda.LongTensor) (:622)
     m = importlib.import_module(script)
     patched, originals = [], {}
     if arm == "repo":

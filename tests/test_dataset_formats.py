@@ -256,3 +256,30 @@ def test_softmask_png_round_trip_through_the_imageio_shim(tmp_path):
     script_side = (imageio.imread(path).astype(np.float32) / 255.0).reshape(-1) > 0
     assert np.array_equal(script_side.reshape(12, 16), mask)
     assert np.array_equal(formats.read_softmask(str(tmp_path), "dtu", "scan21", 3), mask)
+
+
+@needs_ref
+def test_llff_reference_arm_trains_on_the_cpu(tmp_path):
+    """BASELINE config 4's scene and harness without a GPU: twin.make_llff writes an LLFF-format fern stand-in (poses_bounds.npy,
+    images_8/, prior depths in the loader's rescaled units, pairs); the UNMODIFIED run_nerf_view.py -- load_llff_data, hard-mask
+    loop, NDC training (near 0 / far 1), checkpoint, held-out render -- runs on it on the CPU (reference arm only: `.cuda()` made a
+    no-op by the harness; the product has no CPU path).  The hard masks cover most of each training view, i.e. the prior depths
+    are consistent with the recentred poses."""
+    import cv2
+    sys.path.insert(0, ROOT)
+    from oracle import twin
+    if not os.path.isdir(twin.REF):
+        pytest.skip("oracle/_ref not populated")
+    root = str(tmp_path / "llff")
+    twin.make_scene("llff", root)
+    small = ["--use_viewdirs", "--N_samples", "32", "--N_importance", "16", "--N_rand", "512"]
+    res = twin.run_arm_subprocess("ref", "llff", root, iters=4, eval_views=1, eval_res_div=3, extra_args=small, device="cpu", timeout=1500)
+    assert "error" not in res, res
+    assert res["device"] == "cpu" and res["patched"] == [] and res["checkpoints"] == ["000004.tar"]
+    assert res["eval_hw"] == [126, 168] and 3.0 < res["psnr"] < 60.0
+    log = open(os.path.join(root, "log_llff_ref.txt")).read()
+    assert "Loaded llff (20, 378, 504, 3)" in log and "NEAR FAR 0.0 1.0" in log and "TRAIN views are [17, 2, 7, 6, 11, 1]" in log
+    mdir = os.path.join(root, "logs", "twin_fern", "mask", "fern", "6view")
+    cover = {v: float((cv2.imread(os.path.join(mdir, f"{v}_mask_6view.jpg"), 0) > 127).mean()) for v in range(20)}
+    assert all(cover[v] > 0.6 for v in twin.FERN_TRAIN), cover
+    assert all(cover[v] == 0.0 for v in range(20) if v not in twin.FERN_TRAIN)
